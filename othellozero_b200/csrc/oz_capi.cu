@@ -1,0 +1,444 @@
+// oz_capi.cu — the C-ABI (include/oz_b200.h): engine lifetime, search / self-play drivers, net entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include "oz_engine.cuh"
+
+static thread_local char g_err[512] = "";
+
+void oz_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* oz_last_error(void) { return g_err; }
+extern "C" int oz_abi_version(void) { return OZ_ABI_VERSION; }
+
+extern "C" int oz_device_count(int32_t* count) {
+    OZ_REQUIRE(count != nullptr, "count is NULL");
+    int c = 0;
+    cudaError_t err = cudaGetDeviceCount(&c);
+    if (err != cudaSuccess) {
+        *count = 0;
+        oz_set_error("cudaGetDeviceCount failed: %s (this library has no CPU fallback)", cudaGetErrorString(err));
+        return OZ_ERR_CUDA;
+    }
+    *count = c;
+    return OZ_OK;
+}
+
+// ---- small device helpers ---------------------------------------------------------------------------
+__global__ void search_begin_kernel(OzTreeParams P, int num_sims) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.G) return;
+    int st = P.status[g];
+    if (st == OZ_GAME_IDLE || st == OZ_GAME_ACTIVE) {
+        P.status[g] = OZ_GAME_ACTIVE;
+        P.sims_left[g] = num_sims;
+    }
+}
+
+__global__ void scatter_priors_kernel(float* __restrict__ dst, const float* __restrict__ src, int n_leaves, int nsq) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves * nsq) return;
+    int l = i / nsq, f = i - l * nsq;
+    dst[(size_t)l * 64 + f] = src[i];
+}
+
+// ---- engine -----------------------------------------------------------------------------------------
+extern "C" int oz_engine_create(const oz_engine_config* cfg, oz_engine** out) {
+    OZ_REQUIRE(cfg && out, "null argument");
+    *out = nullptr;
+    OZ_REQUIRE(cfg->board_size == 4 || cfg->board_size == 6 || cfg->board_size == 8,
+               "board_size must be 4, 6 or 8 (got %d)", cfg->board_size);
+    OZ_REQUIRE(cfg->max_games >= 1 && cfg->max_games <= (1 << 20), "max_games out of range: %d", cfg->max_games);
+    OZ_REQUIRE(cfg->nodes_per_game >= 2 && cfg->nodes_per_game <= (1 << 22), "nodes_per_game out of range: %d",
+               cfg->nodes_per_game);
+    OZ_REQUIRE(cfg->prior_mode >= OZ_PRIOR_HASH && cfg->prior_mode <= OZ_PRIOR_NET, "bad prior_mode %d", cfg->prior_mode);
+    OZ_REQUIRE(cfg->prior_mode != OZ_PRIOR_NET || cfg->board_size >= 6, "the network needs board_size 6 or 8");
+    int ndev = 0;
+    int rc = oz_device_count(&ndev);
+    if (rc) return rc;
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        oz_set_error("device %d not available (%d CUDA devices; no CPU fallback)", cfg->device, ndev);
+        return OZ_ERR_CUDA;
+    }
+    OZ_CUDA(cudaSetDevice(cfg->device));
+    oz_engine* e = new oz_engine();
+    e->cfg = *cfg;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        oz_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(err));
+        delete e;
+        return OZ_ERR_CUDA;
+    }
+    rc = oz_tree_alloc(e);
+    if (!rc) {
+        err = cudaMallocHost((void**)&e->h_pinned, 64 * sizeof(int));
+        if (err != cudaSuccess) { oz_set_error("cudaMallocHost failed: %s", cudaGetErrorString(err)); rc = OZ_ERR_CUDA; }
+    }
+    if (!rc) rc = oz_net_create(e);
+    if (rc) {
+        oz_engine_destroy(e);
+        return rc;
+    }
+    err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) {
+        oz_set_error("engine init failed: %s", cudaGetErrorString(err));
+        oz_engine_destroy(e);
+        return OZ_ERR_CUDA;
+    }
+    *out = e;
+    return OZ_OK;
+}
+
+extern "C" int oz_engine_destroy(oz_engine* e) {
+    if (!e) return OZ_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    oz_net_destroy(e);
+    for (int i = 0; i < e->n_allocs; ++i) cudaFree(e->allocs[i]);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return OZ_OK;
+}
+
+extern "C" int oz_engine_sync(oz_engine* e) {
+    OZ_REQUIRE(e, "null engine");
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" void* oz_engine_stream(oz_engine* e) { return e ? (void*)e->stream : nullptr; }
+
+extern "C" int oz_engine_counters(oz_engine* e, uint64_t* out8) {
+    OZ_REQUIRE(e && out8, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    OZ_CUDA(cudaMemcpyAsync(out8, e->tp.counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_engine_launches(oz_engine* e, uint64_t* launches) {
+    OZ_REQUIRE(e && launches, "null argument");
+    *launches = e->launches;
+    return OZ_OK;
+}
+
+// ---- search -----------------------------------------------------------------------------------------
+extern "C" int oz_search_reset(oz_engine* e, int32_t n_games, const uint64_t* black, const uint64_t* white,
+                               const int32_t* player, const uint64_t* game_ids) {
+    OZ_REQUIRE(e, "null engine");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    e->tp.selfplay = 0;
+    e->search_started = false;
+    int rc = oz_tree_reset(e, n_games, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
+    if (rc) return rc;
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_search_set_roots(oz_engine* e, const uint64_t* black, const uint64_t* white, const int32_t* player) {
+    OZ_REQUIRE(e && black && white, "null argument");
+    OZ_REQUIRE(e->n_games > 0, "oz_search_reset first");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = oz_tree_reset(e, e->n_games, (const u64*)black, (const u64*)white, player, nullptr, false);
+    if (rc) return rc;
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+static int read_leaf_count(oz_engine* e, int* n) {
+    OZ_CUDA(cudaMemcpyAsync(e->h_pinned, e->tp.leaf_count, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    *n = e->h_pinned[0];
+    return OZ_OK;
+}
+
+// Evaluate the pending leaf batch with the device network (count stays on the device).
+static int eval_leaves_net(oz_engine* e) {
+    return oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games, e->leaf_pi, e->leaf_logits,
+                          e->leaf_v);
+}
+
+static int search_pump(oz_engine* e, int32_t* n_leaves) {
+    OzTreeParams& P = e->tp;
+    const int mode = e->cfg.prior_mode;
+    while (true) {
+        OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
+        int rc = oz_tree_step(e);
+        if (rc) return rc;
+        if (mode == OZ_PRIOR_HASH) { *n_leaves = 0; break; }
+        int nl = 0;
+        if ((rc = read_leaf_count(e, &nl))) return rc;
+        if (nl == 0) { *n_leaves = 0; break; }
+        if (mode == OZ_PRIOR_HOST) { e->host_leaves = nl; *n_leaves = nl; return OZ_OK; }
+        if ((rc = eval_leaves_net(e))) return rc;
+    }
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    e->host_leaves = 0;
+    return OZ_OK;
+}
+
+extern "C" int oz_search_begin(oz_engine* e, int32_t num_sims, int32_t* n_leaves) {
+    OZ_REQUIRE(e && n_leaves, "null argument");
+    OZ_REQUIRE(num_sims >= 1, "num_sims must be >= 1");
+    if (e->n_games <= 0) { oz_set_error("oz_search_reset first"); return OZ_ERR_STATE; }
+    if (e->host_leaves) { oz_set_error("pending leaves have not been answered"); return OZ_ERR_STATE; }
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    e->tp.selfplay = 0;
+    search_begin_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, num_sims);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    return search_pump(e, n_leaves);
+}
+
+extern "C" int oz_search_continue(oz_engine* e, int32_t* n_leaves) {
+    OZ_REQUIRE(e && n_leaves, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    if (e->host_leaves) { oz_set_error("pending leaves have not been answered (oz_search_put_priors)"); return OZ_ERR_STATE; }
+    return search_pump(e, n_leaves);
+}
+
+extern "C" int oz_search_get_leaves(oz_engine* e, uint64_t* own, uint64_t* opp, int32_t n_leaves) {
+    OZ_REQUIRE(e && own && opp, "null argument");
+    OZ_REQUIRE(n_leaves >= 0 && n_leaves <= e->host_leaves, "n_leaves %d > pending %d", n_leaves, e->host_leaves);
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    OZ_CUDA(cudaMemcpyAsync(own, e->tp.leaf_own, (size_t)n_leaves * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(opp, e->tp.leaf_opp, (size_t)n_leaves * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_search_put_priors(oz_engine* e, const float* pi, const float* v, int32_t n_leaves) {
+    OZ_REQUIRE(e && pi && v, "null argument");
+    if (n_leaves != e->host_leaves) {
+        oz_set_error("expected priors for %d leaves, got %d", e->host_leaves, n_leaves);
+        return OZ_ERR_STATE;
+    }
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    const int nsq = e->tp.nsq;
+    float* tmp = nullptr;
+    OZ_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n_leaves * nsq * sizeof(float), e->stream));
+    OZ_CUDA(cudaMemcpyAsync(tmp, pi, (size_t)n_leaves * nsq * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    scatter_priors_kernel<<<(n_leaves * nsq + 255) / 256, 256, 0, e->stream>>>(e->leaf_pi, tmp, n_leaves, nsq);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    OZ_CUDA(cudaMemcpyAsync(e->leaf_v, v, (size_t)n_leaves * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    OZ_CUDA(cudaFreeAsync(tmp, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    e->host_leaves = 0;
+    return OZ_OK;
+}
+
+extern "C" int oz_search_get_visits(oz_engine* e, int32_t* visits, int32_t* ns) {
+    OZ_REQUIRE(e && visits && ns, "null argument");
+    OZ_REQUIRE(e->n_games > 0, "oz_search_reset first");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    int* dv = nullptr;
+    size_t nv = (size_t)e->n_games * 64;
+    OZ_CUDA(cudaMallocAsync((void**)&dv, (nv + e->n_games) * sizeof(int), e->stream));
+    int rc = oz_tree_visits(e, dv, dv + nv);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(visits, dv, nv * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(ns, dv + nv, (size_t)e->n_games * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaFreeAsync(dv, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_search_get_root_stats(oz_engine* e, int32_t game, double* q, double* p, int32_t* qtag) {
+    OZ_REQUIRE(e && q && p && qtag, "null argument");
+    OZ_REQUIRE(game >= 0 && game < e->n_games, "game %d out of range", game);
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    double* dq = nullptr;
+    OZ_CUDA(cudaMallocAsync((void**)&dq, 128 * sizeof(double) + 72 * sizeof(int), e->stream));
+    int* dt = (int*)(dq + 128);
+    int rc = oz_tree_root_stats(e, game, dq, dq + 64, dt);
+    if (rc) return rc;
+    int found = -1;
+    OZ_CUDA(cudaMemcpyAsync(q, dq, 64 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(p, dq + 64, 64 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(qtag, dt, 64 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(&found, dt + 64, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaFreeAsync(dq, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    if (found < 0) { oz_set_error("root of game %d is not in the tree", game); return OZ_ERR_STATE; }
+    return OZ_OK;
+}
+
+extern "C" int oz_search_get_status(oz_engine* e, int32_t* status) {
+    OZ_REQUIRE(e && status, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    OZ_CUDA(cudaMemcpyAsync(status, e->tp.status, (size_t)e->n_games * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+// ---- self-play --------------------------------------------------------------------------------------
+extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* black, const uint64_t* white,
+                                 const int32_t* player, const uint64_t* game_ids, int32_t num_sims, double temperature,
+                                 double e_greedy, int32_t max_moves) {
+    OZ_REQUIRE(e, "null engine");
+    OZ_REQUIRE(num_sims >= 2, "num_sims must be >= 2 (with 1 the reference's policy is all-zero, training.py:48-53)");
+    OZ_REQUIRE(temperature > 0.0, "device self-play needs temperature > 0 (T=0 draws random.choice, othelo_mcts.py:54-62)");
+    OZ_REQUIRE(e_greedy >= 0.0 && e_greedy <= 1.0, "e_greedy must be in [0,1]");
+    if (e->cfg.prior_mode == OZ_PRIOR_HOST) { oz_set_error("self-play needs OZ_PRIOR_HASH or OZ_PRIOR_NET"); return OZ_ERR_STATE; }
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = oz_tree_reset(e, n_games, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
+    if (rc) return rc;
+    OzTreeParams& P = e->tp;
+    P.selfplay = 1;
+    P.num_sims = num_sims;
+    P.max_moves = max_moves;
+    P.e_greedy = e_greedy;
+    e->h_pinned[1] = n_games;
+    OZ_CUDA(cudaMemcpyAsync(P.n_active, &e->h_pinned[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.rec_action, 0xFF, (size_t)n_games * 64, e->stream));
+    search_begin_kernel<<<(P.G + 255) / 256, 256, 0, e->stream>>>(P, num_sims);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    e->search_started = true;
+    return OZ_OK;
+}
+
+extern "C" int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active) {
+    OZ_REQUIRE(e, "null engine");
+    if (!e->search_started || !e->tp.selfplay) { oz_set_error("oz_selfplay_begin first"); return OZ_ERR_STATE; }
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    OzTreeParams& P = e->tp;
+    const bool net = e->cfg.prior_mode == OZ_PRIOR_NET;
+    int active = -1;
+    long long done = 0;
+    u64 last_sims = ~0ull;
+    u64* h_sims = (u64*)&e->h_pinned[8];
+    while (steps < 0 || done < steps) {
+        long long chunk = (steps < 0) ? 64 : (long long)steps - done;
+        if (chunk > 64) chunk = 64;
+        for (long long s = 0; s < chunk; ++s) {
+            OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
+            int rc = oz_tree_step(e);
+            if (rc) return rc;
+            if (net && (rc = eval_leaves_net(e))) return rc;
+        }
+        done += chunk;
+        OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[2], P.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(h_sims, P.counters, sizeof(u64), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        active = e->h_pinned[2];
+        if (active <= 0) break;
+        // a pool-exhausted game never finishes: report it instead of spinning forever
+        if (steps < 0 && *h_sims == last_sims) {
+            oz_set_error("self-play stalled with %d games active (node pool exhausted?)", active);
+            return OZ_ERR_NOMEM;
+        }
+        last_sims = *h_sims;
+    }
+    if (active < 0) {
+        OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[2], P.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        active = e->h_pinned[2];
+    }
+    if (n_active) *n_active = active;
+    return OZ_OK;
+}
+
+extern "C" int oz_selfplay_get_records(oz_engine* e, uint64_t* rec_black, uint64_t* rec_white, uint8_t* rec_action,
+                                       uint8_t* rec_player, int32_t* n_moves, int32_t* winner, int32_t* rec_visits) {
+    OZ_REQUIRE(e && rec_black && rec_white && rec_action && rec_player && n_moves && winner, "null argument");
+    OZ_REQUIRE(e->n_games > 0, "no games");
+    OZ_REQUIRE(!rec_visits || e->cfg.log_visits, "engine was created without log_visits");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    OzTreeParams& P = e->tp;
+    size_t g = (size_t)e->n_games;
+    OZ_CUDA(cudaMemcpyAsync(rec_black, P.rec_black, g * 64 * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(rec_white, P.rec_white, g * 64 * 8, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(rec_action, P.rec_action, g * 64, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(rec_player, P.rec_player, g * 64, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(n_moves, P.ply, g * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(winner, P.winner, g * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (rec_visits) OZ_CUDA(cudaMemcpyAsync(rec_visits, P.rec_visits, g * 64 * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_selfplay_get_positions(oz_engine* e, uint64_t* black, uint64_t* white, int32_t* player) {
+    OZ_REQUIRE(e, "null engine");
+    OZ_REQUIRE(e->n_games > 0, "no games");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    size_t g = (size_t)e->n_games;
+    if (black) OZ_CUDA(cudaMemcpyAsync(black, e->tp.black, g * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (white) OZ_CUDA(cudaMemcpyAsync(white, e->tp.white, g * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (player) OZ_CUDA(cudaMemcpyAsync(player, e->tp.player, g * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+// ---- network ----------------------------------------------------------------------------------------
+extern "C" int64_t oz_net_blob_floats(int32_t board_size, int32_t channels) {
+    return oz_net_blob_floats_impl(board_size, channels);
+}
+
+extern "C" int oz_net_load_weights(oz_engine* e, const float* blob, int64_t n_floats, int32_t channels) {
+    OZ_REQUIRE(e && blob, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    return oz_net_load(e, blob, n_floats, channels, false);
+}
+
+extern "C" int oz_net_load_weights_dev(oz_engine* e, const float* blob_dev, int64_t n_floats, int32_t channels) {
+    OZ_REQUIRE(e && blob_dev, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    return oz_net_load(e, blob_dev, n_floats, channels, true);
+}
+
+extern "C" int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint64_t* opp, int32_t n, float* pi,
+                                  float* logits, float* v) {
+    OZ_REQUIRE(e && own && opp && pi && v, "null argument");
+    OZ_REQUIRE(n >= 1 && n <= e->cfg.max_games, "n %d out of range (max_games %d)", n, e->cfg.max_games);
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    e->h_pinned[3] = n;
+    int* cnt = e->tp.leaf_count + 1;
+    OZ_CUDA(cudaMemcpyAsync(cnt, &e->h_pinned[3], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    int rc = oz_net_forward(e, (const u64*)own, (const u64*)opp, cnt, n, pi, logits ? logits : e->leaf_logits, v);
+    if (rc) return rc;
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_net_forward_host(oz_engine* e, const uint64_t* own, const uint64_t* opp, int32_t n, float* pi,
+                                   float* logits, float* v) {
+    OZ_REQUIRE(e && own && opp && pi && v, "null argument");
+    OZ_REQUIRE(n >= 1 && n <= e->cfg.max_games, "n %d out of range (max_games %d)", n, e->cfg.max_games);
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    const int nsq = e->tp.nsq;
+    OZ_CUDA(cudaMemcpyAsync(e->tp.leaf_own, own, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(e->tp.leaf_opp, opp, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+    e->h_pinned[3] = n;
+    int* cnt = e->tp.leaf_count + 1;
+    OZ_CUDA(cudaMemcpyAsync(cnt, &e->h_pinned[3], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, cnt, n, e->leaf_pi, e->leaf_logits, e->leaf_v);
+    if (rc) return rc;
+    // device rows have stride 64; host rows are N*N contiguous
+    OZ_CUDA(cudaMemcpy2DAsync(pi, (size_t)nsq * 4, e->leaf_pi, 64 * 4, (size_t)nsq * 4, n, cudaMemcpyDeviceToHost, e->stream));
+    if (logits)
+        OZ_CUDA(cudaMemcpy2DAsync(logits, (size_t)nsq * 4, e->leaf_logits, 64 * 4, (size_t)nsq * 4, n, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(v, e->leaf_v, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}
+
+extern "C" int oz_net_layer_times(oz_engine* e, float* ms8) {
+    OZ_REQUIRE(e && ms8, "null argument");
+    memcpy(ms8, e->layer_ms, sizeof(e->layer_ms));
+    return OZ_OK;
+}
+
+extern "C" int oz_net_get_activation(oz_engine* e, int32_t layer, void* host_bf16, int64_t bytes) {
+    OZ_REQUIRE(e && host_bf16, "null argument");
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    return oz_net_activation(e, layer, host_bf16, bytes);
+}

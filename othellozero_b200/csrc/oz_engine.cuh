@@ -1,0 +1,135 @@
+// oz_engine.cuh — internal engine state shared by the tree, net and C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/oz_b200.h"
+#include "oz_bitboard.cuh"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---- error plumbing ------------------------------------------------------------------------
+void oz_set_error(const char* fmt, ...);
+#define OZ_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            oz_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return OZ_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+#define OZ_REQUIRE(cond, ...)        \
+    do {                             \
+        if (!(cond)) {               \
+            oz_set_error(__VA_ARGS__); \
+            return OZ_ERR_INVALID;   \
+        }                            \
+    } while (0)
+
+// ---- tree node pool layout (HBM) -----------------------------------------------------------------
+// Node = 48-byte header followed by SoA child rows, k = popcount(legal):
+//   double P[k]; double Q[k]; int N[k]; int child[k];        (48 + 24k bytes, rounded up to 16)
+// Child slot j <-> j-th set bit of `legal` (ascending == reference row-major action order).
+// Node references are offsets into the game's arena in 16-byte units.
+struct __align__(16) OzNodeHdr {
+    u64 own, opp;  // canonical key (exact board; MCTS/__init__.py:7-16 hashes the board bytes)
+    u64 legal;     // cached get_state_actions (MCTS/__init__.py:183-187)
+    u64 qf32;      // bit j: Q[j] currently has numpy float32 type (else python float / int 0)
+    int ns;        // _Ns
+    int k;
+    int pad0, pad1;
+};
+static_assert(sizeof(OzNodeHdr) == 48, "node header layout");
+
+constexpr int OZ_CH_UNKNOWN = -1;   // edge never traversed
+constexpr int OZ_CH_TERM_NEG = -2;  // child is terminal, simulate() returns -1
+constexpr int OZ_CH_TERM_POS = -3;  // child is terminal, simulate() returns +1
+constexpr int OZ_MAX_DEPTH = 64;
+
+struct OzTreeParams {
+    int n;          // board size
+    int nsq;        // n*n
+    u64 full;       // full_mask(n)
+    int G;          // active game slots
+    int prior_mode;
+    int selfplay;   // 1: move transitions happen on device
+    int log_visits;
+    double c;
+    // per-slot state
+    u64* black; u64* white; int* player;
+    int* status; int* root_node; int* sims_left; int* ply; u64* game_id; int* winner;
+    // pending leaf (WAIT_LEAF)
+    u64* pend_own; u64* pend_opp; u64* pend_legal;
+    int* pend_parent; int* pend_edge; int* pend_depth; int* pend_leaf;
+    u32* path_node; u32* path_edge;  // [G][64]
+    // pools
+    unsigned char* arena; u64 arena_stride;  // bytes per game
+    u32* bump;                                // next free offset (16-byte units) per game
+    u64* table; int table_log2;               // [G][1<<table_log2] : fingerprint<<32 | (node_off+1)
+    // leaf batch
+    u64* leaf_own; u64* leaf_opp; int* leaf_count; const float* leaf_pi; const float* leaf_v;
+    // self-play
+    int num_sims; int max_moves; double e_greedy; u64 seed;
+    u64* rec_black; u64* rec_white; unsigned char* rec_action; unsigned char* rec_player; int* rec_visits;
+    // counters (device)
+    u64* counters;  // see oz_engine_counters
+    int* n_active;
+};
+
+struct OzNet;  // oz_net.cu
+
+struct oz_engine {
+    oz_engine_config cfg;
+    cudaStream_t stream = nullptr;
+    OzTreeParams tp{};
+    int n_games = 0;
+    bool search_started = false;
+    int host_leaves = 0;
+    int table_log2 = 0;
+    u64 arena_stride = 0;
+    u64 launches = 0;
+    // device allocations (freed in destroy)
+    void* allocs[64];
+    int n_allocs = 0;
+    float* leaf_pi = nullptr;  // [max_games][64]
+    float* leaf_v = nullptr;
+    float* leaf_logits = nullptr;
+    int* h_pinned = nullptr;   // small pinned scratch
+    OzNet* net = nullptr;
+    float layer_ms[8] = {0};
+};
+
+// tree (oz_tree.cu)
+int oz_tree_alloc(oz_engine* e);
+int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white, const int* player, const u64* ids,
+                  bool clear);
+int oz_tree_step(oz_engine* e);  // one tree kernel launch
+int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev);
+int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev);
+
+// net (oz_net.cu)
+int oz_net_create(oz_engine* e);
+void oz_net_destroy(oz_engine* e);
+int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels, bool on_device);
+// forward over `count_dev` (device int, <= max_games) canonical boards -> e->leaf_pi / leaf_logits / leaf_v
+int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const int* count_dev, int max_count,
+                   float* pi_dev, float* logits_dev, float* v_dev);
+int64_t oz_net_blob_floats_impl(int board_size, int channels);
+int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes);
+
+template <typename T>
+int oz_dev_alloc(oz_engine* e, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (err != cudaSuccess) {
+        oz_set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
+        return OZ_ERR_NOMEM;
+    }
+    if (e->n_allocs >= 64) { oz_set_error("too many allocations"); return OZ_ERR_NOMEM; }
+    e->allocs[e->n_allocs++] = q;
+    *p = (T*)q;
+    return OZ_OK;
+}

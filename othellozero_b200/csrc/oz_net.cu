@@ -1,0 +1,708 @@
+// oz_net.cu — K7..K10: the OthelloNNet policy/value tower (Net/OthelloNN.py:42-52) as bf16 tcgen05 kernels.
+//
+//   conv1 (Cin=2)     : the 3x3x2 binary input patch has only 3^9 = 19683 states, so conv1+BN+ReLU is a
+//                       pre-computed 19683 x C bf16 table (built at weight load) and the layer is a pure
+//                       gather from the L2-resident table (K7 fused with conv1).  HBM-write bound.
+//   conv2..4, fc1, fc2: ONE persistent, warp-specialised implicit-GEMM kernel:
+//                       TMA (4-D tiled tensor map over the NHWC activation; taps = shifted boxes with
+//                       hardware zero fill for padding='same') -> 128B-swizzled smem ring ->
+//                       tcgen05.mma (128 x BLOCK_N x 16, bf16 in / fp32 accumulate in TMEM, double
+//                       buffered) -> tcgen05.ld epilogue: + folded BN bias, ReLU, bf16 store.
+//   heads             : same kernel, BLOCK_N = 128 (N^2 policy logits + 1 value row), epilogue = row
+//                       softmax + tanh (Net/OthelloNN.py:50-52).  The net returns PROBABILITIES
+//                       (NNetWrapper.predict, Net/NNet.py:85-87); logits are exposed for the parity check.
+//
+// BatchNormalization (eps 1e-3, moving statistics, Net/OthelloNN.py:43-49) is folded into the weights
+// (fp32, then cast to bf16) and a per-channel fp32 bias at load time.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "oz_engine.cuh"
+
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int GEMM_THREADS = 256;
+constexpr int EPI_RELU_BF16 = 0;
+constexpr int EPI_HEADS = 1;
+constexpr int N_PATTERNS = 19683;  // 3^9
+
+struct GemmParams {
+    int num_kb;          // K / 64
+    int chunks_per_tap;  // Cin / 64 (conv) or num_kb (fc)
+    int ntaps_x;         // 3 (conv) or 1 (fc)
+    int pad;             // 1: padding='same', 0: 'valid' / fc
+    int nb;              // boards per M tile
+    int rows_per_board;  // OH*OW (1 for fc)
+    int rows_valid;      // nb * rows_per_board (<= 128)
+    int n_tiles;         // Nout / BLOCK_N
+    int ldc;             // output row stride in elements
+    int max_count;
+    unsigned a_bytes;    // TMA bytes per A stage
+    const int* count;    // device: number of boards in this batch
+    const float* bias;   // [Nout] fp32 (BN folded)
+    bf16* out;
+    float* pi; float* logits; float* v;  // heads
+    int nsq;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 27)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; bf16 x bf16 -> fp32, both operands K-major.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BLOCK_N>
+struct GemmSmem {
+    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = STAGES * A_STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_B + STAGES * B_STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2]
+    static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
+    static constexpr int OFF_BIAS = OFF_TMEM + 16;                    // [2][BLOCK_N] floats
+    static constexpr int BYTES = OFF_BIAS + 2 * BLOCK_N * 4;
+    static constexpr int DYN_BYTES = BYTES + 1024;                    // manual 1024-byte alignment slack
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    using S = GemmSmem<BLOCK_N>;
+    constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + S::OFF_A, sB = base + S::OFF_B, sBar = base + S::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return sBar + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return sBar + 8u * (2 * STAGES + 2 + a); };
+    volatile uint32_t* s_tmem = (volatile uint32_t*)(gbase + S::OFF_TMEM);
+    float* s_bias = (float*)(gbase + S::OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int L = *p.count;
+    if (L > p.max_count) L = p.max_count;
+    const int m_tiles = (L + p.nb - 1) / p.nb;
+    const int num_tiles = m_tiles * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32((const void*)s_tmem), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / p.n_tiles, n_idx = tile - m_tile * p.n_tiles;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), p.a_bytes + (unsigned)B_STAGE_BYTES);
+                    const int tap = kb / p.chunks_per_tap, chunk = kb - tap * p.chunks_per_tap;
+                    const int ky = tap / p.ntaps_x, kx = tap - ky * p.ntaps_x;
+                    tma_load_4d(sA + stage * A_STAGE_BYTES, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad,
+                                m_tile * p.nb);
+                    tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, full_bar(stage), kb * BLOCK_K, n_idx * BLOCK_N);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer (single thread) =====
+            constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
+                    const uint64_t bdesc = make_sw128_desc(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // advance the start address by k*32 bytes inside the 128-byte swizzle row
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may access
+        const int et = threadIdx.x - 128;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_tile = tile / p.n_tiles, n_idx = tile - m_tile * p.n_tiles;
+            float* bias = s_bias + acc * BLOCK_N;
+            for (int i = et; i < BLOCK_N; i += 128) bias[i] = p.bias[n_idx * BLOCK_N + i];
+            epi_bar_sync();
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int r = ew * 32 + lane;
+            const long long grow = (long long)m_tile * p.rows_valid + r;
+            const bool ok = (r < p.rows_valid) && (grow < (long long)L * p.rows_per_board);
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
+            if constexpr (EPI == EPI_RELU_BF16) {
+                bf16* orow = p.out + grow * p.ldc + (long long)n_idx * BLOCK_N;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    if (ok) {
+                        uint32_t packed[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], 0.0f);
+                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.0f);
+                            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    }
+                }
+            } else {
+                // heads: columns [0,nsq) = policy logits, column nsq = value pre-activation
+                float lg[96];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) lg[c * 32 + j] = __uint_as_float(v[j]) + bias[c * 32 + j];
+                }
+                if (ok) {
+                    const int nsq = p.nsq;
+                    float mx = -3.0e38f;
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) if (j < nsq) mx = fmaxf(mx, lg[j]);
+                    float sum = 0.f;
+                    float ex[64];
+#pragma unroll
+                    for (int j = 0; j < 64; ++j) { ex[j] = (j < nsq) ? expf(lg[j] - mx) : 0.f; sum += ex[j]; }
+                    const float inv = 1.0f / sum;
+                    float* lrow = p.logits + grow * 64;
+                    float* prow = p.pi + grow * 64;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4) {
+                        *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
+                        *reinterpret_cast<float4*>(prow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                    }
+                    p.v[grow] = tanhf(nsq == 64 ? lg[64] : lg[36]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- conv1 as a table gather -------------------------------------------------------------------------
+// table[pattern][co] = relu(b' + sum_t [s_t==own] W'[t][0][co] + [s_t==opp] W'[t][1][co]), pattern = sum s_t 3^t,
+// t = ky*3+kx (cross-correlation, Keras Conv2D), s = 0 empty / outside the board (zero padding), 1 own, 2 opp.
+__global__ void conv1_table_kernel(const float* __restrict__ w1 /*[9][2][C]*/, const float* __restrict__ b1,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
+                                   bf16* __restrict__ table) {
+    int pat = blockIdx.x;
+    int digits[9];
+    int x = pat;
+    for (int t = 0; t < 9; ++t) { digits[t] = x % 3; x /= 3; }
+    for (int co = threadIdx.x; co < C; co += blockDim.x) {
+        float s = gamma[co] / sqrtf(var[co] + eps);
+        float acc = 0.f;
+        for (int t = 0; t < 9; ++t)
+            if (digits[t]) acc += w1[(t * 2 + (digits[t] - 1)) * C + co];
+        float y = (acc + b1[co] - mean[co]) * s + beta[co];
+        table[(size_t)pat * C + co] = __float2bfloat16(fmaxf(y, 0.f));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+conv1_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count, int max_count,
+                    int n, int C, const bf16* __restrict__ table, bf16* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int L = *count;
+    if (L > max_count) L = max_count;
+    const int nsq = n * n;
+    if (w >= (long long)L * nsq) return;
+    const int b = (int)(w / nsq), pos = (int)(w - (long long)b * nsq);
+    const int y = pos / n, x = pos - y * n;
+    const u64 o = own[b], q = opp[b];
+    int pat = 0, mul = 1;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+        int s = 0;
+        if (yy >= 0 && yy < n && xx >= 0 && xx < n) {
+            const int bit = yy * 8 + xx;
+            s = (int)((o >> bit) & 1ull) + 2 * (int)((q >> bit) & 1ull);
+        }
+        pat += s * mul;
+        mul *= 3;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)pat * C);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)w * C);
+    for (int i = lane; i < C / 8; i += 32) dst[i] = __ldg(src + i);
+}
+
+// ---- weight folding -------------------------------------------------------------------------------------
+// Keras kernel W[k][o] (HWIO flattened / Dense (in,out)) -> Wt[o][k] bf16 with the BN scale folded;
+// bias'[o] = (b - mean) * s + beta.
+__global__ void fold_weights_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, int K, int Nout, bf16* __restrict__ Wt,
+                                    float* __restrict__ bias_out) {
+    __shared__ float tile[32][33];
+    const int k0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int k = k0 + i, o = o0 + threadIdx.x;
+        tile[i][threadIdx.x] = (k < K && o < Nout) ? W[(size_t)k * Nout + o] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int o = o0 + i, k = k0 + threadIdx.x;
+        if (o < Nout && k < K) {
+            float s = gamma ? gamma[o] / sqrtf(var[o] + eps) : 1.0f;
+            Wt[(size_t)o * K + k] = __float2bfloat16(tile[threadIdx.x][i] * s);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.y == 0) {
+        int o = o0 + threadIdx.x;
+        if (o < Nout) {
+            float s = gamma ? gamma[o] / sqrtf(var[o] + eps) : 1.0f;
+            bias_out[o] = gamma ? (b[o] - mean[o]) * s + beta[o] : b[o];
+        }
+    }
+}
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_tmapEncodeTiled get_encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
+}  // namespace
+
+struct OzLayer {
+    CUtensorMap mapA, mapB;
+    GemmParams p;
+    int block_n;
+    int epi;
+    int max_tiles;
+    double flops_per_board;
+};
+
+struct OzNet {
+    int n = 0, C = 0, Bmax = 0;
+    bool loaded = false;
+    bool timing = false;
+    int sm_count = 148;
+    bf16* table1 = nullptr;
+    bf16 *w[6] = {nullptr}; float* bias[6] = {nullptr};  // conv2, conv3, conv4, fc1, fc2, heads
+    bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *act4 = nullptr, *f1 = nullptr, *f2 = nullptr;
+    OzLayer layer[6];
+    cudaEvent_t ev[8] = {nullptr};
+    void* allocs[32];
+    int n_allocs = 0;
+};
+
+static int net_alloc(OzNet* net, void** p, size_t bytes) {
+    cudaError_t err = cudaMalloc(p, bytes + 256);
+    if (err != cudaSuccess) { oz_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err)); return OZ_ERR_NOMEM; }
+    net->allocs[net->n_allocs++] = *p;
+    return OZ_OK;
+}
+
+int64_t oz_net_blob_floats_impl(int n, int C) {
+    if ((n != 6 && n != 8) || C <= 0) return -1;
+    int64_t nsq = n * n, k1 = (int64_t)(n - 4) * (n - 4) * C;
+    int64_t t = 0;
+    t += 18LL * C + C + 4LL * C;                 // conv1 + bn1
+    t += 3 * (9LL * C * C + C + 4LL * C);        // conv2..4 + bn
+    t += k1 * 1024 + 1024 + 4 * 1024;            // fc1 + bn5
+    t += 1024LL * 512 + 512 + 4 * 512;           // fc2 + bn6
+    t += 512 * nsq + nsq;                        // pi
+    t += 512 + 1;                                // v
+    return t;
+}
+
+int oz_net_create(oz_engine* e) {
+    e->net = nullptr;
+    if (e->cfg.prior_mode != OZ_PRIOR_NET) return OZ_OK;
+    OzNet* net = new OzNet();
+    net->n = e->cfg.board_size;
+    net->Bmax = e->cfg.max_games;
+    const char* t = getenv("OZ_NET_TIMING");
+    net->timing = t && t[0] == '1';
+    int dev = e->cfg.device;
+    cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&net->ev[i]);
+    e->net = net;
+    return OZ_OK;
+}
+
+void oz_net_destroy(oz_engine* e) {
+    OzNet* net = e->net;
+    if (!net) return;
+    for (int i = 0; i < net->n_allocs; ++i) cudaFree(net->allocs[i]);
+    for (int i = 0; i < 8; ++i) if (net->ev[i]) cudaEventDestroy(net->ev[i]);
+    delete net;
+    e->net = nullptr;
+}
+
+static int make_map_A(CUtensorMap* m, bf16* base, int Cdim, int W, int H, int B, int bw, int bh, int nb) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) { oz_set_error("cuTensorMapEncodeTiled entry point not available"); return OZ_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)Cdim, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)Cdim * 2, (cuuint64_t)Cdim * 2 * W, (cuuint64_t)Cdim * 2 * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)nb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { oz_set_error("cuTensorMapEncodeTiled(A) failed: %d", (int)r); return OZ_ERR_CUDA; }
+    return OZ_OK;
+}
+
+static int make_map_B(CUtensorMap* m, bf16* base, int K, int Nout, int block_n) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) { oz_set_error("cuTensorMapEncodeTiled entry point not available"); return OZ_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Nout};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { oz_set_error("cuTensorMapEncodeTiled(B) failed: %d", (int)r); return OZ_ERR_CUDA; }
+    return OZ_OK;
+}
+
+// layer li: input [B][ih][iw][cin] -> output [B][oh*ow][nout]; ntaps 3 (conv) or 1 (fc)
+static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, int ow, int oh, int ntaps, int pad, int nout_pad,
+                       int block_n, int epi, bf16* out, int ldc) {
+    OzLayer& Lr = net->layer[li];
+    GemmParams& p = Lr.p;
+    memset(&p, 0, sizeof(p));
+    const int rows_per_board = ow * oh;
+    int nb = BLOCK_M / rows_per_board;
+    if (nb > 256) nb = 256;
+    p.nb = nb;
+    p.rows_per_board = rows_per_board;
+    p.rows_valid = nb * rows_per_board;
+    p.ntaps_x = ntaps;
+    p.pad = pad;
+    p.chunks_per_tap = cin / BLOCK_K;
+    p.num_kb = ntaps * ntaps * p.chunks_per_tap;
+    p.n_tiles = nout_pad / block_n;
+    p.ldc = ldc;
+    p.max_count = net->Bmax;
+    p.a_bytes = (unsigned)(p.rows_valid * BLOCK_K * 2);
+    p.bias = net->bias[li];
+    p.out = out;
+    p.nsq = net->n * net->n;
+    Lr.block_n = block_n;
+    Lr.epi = epi;
+    Lr.max_tiles = ((net->Bmax + nb - 1) / nb) * p.n_tiles;
+    int rc = make_map_A(&Lr.mapA, in, cin, iw, ih, net->Bmax, ow, oh, nb);
+    if (rc) return rc;
+    return make_map_B(&Lr.mapB, net->w[li], ntaps * ntaps * cin, nout_pad, block_n);
+}
+
+int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels, bool on_device) {
+    OzNet* net = e->net;
+    if (!net) { oz_set_error("engine was not created with OZ_PRIOR_NET"); return OZ_ERR_STATE; }
+    const int n = net->n, C = channels, nsq = n * n, B = net->Bmax;
+    OZ_REQUIRE(C >= 64 && C % 64 == 0 && C <= 1024, "channels must be a multiple of 64 in [64,1024] (got %d)", C);
+    const int64_t need = oz_net_blob_floats_impl(n, C);
+    OZ_REQUIRE(n_floats == need, "weight blob has %lld floats, expected %lld", (long long)n_floats, (long long)need);
+    if (net->loaded && net->C != C) { oz_set_error("channel count cannot change after the first load"); return OZ_ERR_STATE; }
+    cudaStream_t st = e->stream;
+    const int o2 = n - 2, o4 = n - 4;
+    const int K1 = o4 * o4 * C;
+    int rc;
+    if (!net->loaded) {
+        net->C = C;
+        const size_t kc = 9ull * C * C;
+#define NA(ptr, bytes) if ((rc = net_alloc(net, (void**)&(ptr), (bytes)))) return rc;
+        NA(net->table1, (size_t)N_PATTERNS * C * 2)
+        NA(net->w[0], kc * 2) NA(net->w[1], kc * 2) NA(net->w[2], kc * 2)
+        NA(net->w[3], (size_t)K1 * 1024 * 2) NA(net->w[4], 1024ull * 512 * 2) NA(net->w[5], 128ull * 512 * 2)
+        NA(net->bias[0], C * 4) NA(net->bias[1], C * 4) NA(net->bias[2], C * 4)
+        NA(net->bias[3], 1024 * 4) NA(net->bias[4], 512 * 4) NA(net->bias[5], 128 * 4)
+        NA(net->act1, (size_t)B * nsq * C * 2) NA(net->act2, (size_t)B * nsq * C * 2)
+        NA(net->act3, (size_t)B * o2 * o2 * C * 2) NA(net->act4, (size_t)B * o4 * o4 * C * 2)
+        NA(net->f1, (size_t)B * 1024 * 2) NA(net->f2, (size_t)B * 512 * 2)
+#undef NA
+        if ((rc = setup_layer(net, 0, net->act1, C, n, n, n, n, 3, 1, C, 256, EPI_RELU_BF16, net->act2, C))) return rc;
+        if ((rc = setup_layer(net, 1, net->act2, C, n, n, o2, o2, 3, 0, C, 256, EPI_RELU_BF16, net->act3, C))) return rc;
+        if ((rc = setup_layer(net, 2, net->act3, C, o2, o2, o4, o4, 3, 0, C, 256, EPI_RELU_BF16, net->act4, C))) return rc;
+        if ((rc = setup_layer(net, 3, net->act4, K1, 1, 1, 1, 1, 1, 0, 1024, 256, EPI_RELU_BF16, net->f1, 1024))) return rc;
+        if ((rc = setup_layer(net, 4, net->f1, 1024, 1, 1, 1, 1, 1, 0, 512, 256, EPI_RELU_BF16, net->f2, 512))) return rc;
+        if ((rc = setup_layer(net, 5, net->f2, 512, 1, 1, 1, 1, 1, 0, 128, 128, EPI_HEADS, nullptr, 64))) return rc;
+        OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<256, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmSmem<256>::DYN_BYTES));
+        OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmSmem<128>::DYN_BYTES));
+        OZ_CUDA(cudaMemsetAsync(net->w[5], 0, 128ull * 512 * 2, st));
+        OZ_CUDA(cudaMemsetAsync(net->bias[5], 0, 128 * 4, st));
+    }
+    // stage the blob on the device
+    const float* d = blob;
+    float* staged = nullptr;
+    if (!on_device) {
+        OZ_CUDA(cudaMallocAsync((void**)&staged, (size_t)need * 4, st));
+        OZ_CUDA(cudaMemcpyAsync(staged, blob, (size_t)need * 4, cudaMemcpyHostToDevice, st));
+        d = staged;
+    }
+    const float eps = 1e-3f;  // keras BatchNormalization default epsilon
+    const float* q = d;
+    auto take = [&](int64_t cnt) { const float* r = q; q += cnt; return r; };
+    dim3 tb(32, 8);
+    {   // conv1 + bn1 -> table
+        const float* w1 = take(18LL * C); const float* b1 = take(C);
+        const float* g = take(C); const float* be = take(C); const float* mu = take(C); const float* va = take(C);
+        conv1_table_kernel<<<N_PATTERNS, 256, 0, st>>>(w1, b1, g, be, mu, va, eps, C, net->table1);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    for (int li = 0; li < 3; ++li) {  // conv2..4
+        const int K = 9 * C;
+        const float* w = take((int64_t)K * C); const float* b = take(C);
+        const float* g = take(C); const float* be = take(C); const float* mu = take(C); const float* va = take(C);
+        fold_weights_kernel<<<dim3((K + 31) / 32, (C + 31) / 32), tb, 0, st>>>(w, b, g, be, mu, va, eps, K, C, net->w[li], net->bias[li]);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    {   // fc1 + bn5
+        const float* w = take((int64_t)K1 * 1024); const float* b = take(1024);
+        const float* g = take(1024); const float* be = take(1024); const float* mu = take(1024); const float* va = take(1024);
+        fold_weights_kernel<<<dim3((K1 + 31) / 32, 32), tb, 0, st>>>(w, b, g, be, mu, va, eps, K1, 1024, net->w[3], net->bias[3]);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    {   // fc2 + bn6
+        const float* w = take(1024LL * 512); const float* b = take(512);
+        const float* g = take(512); const float* be = take(512); const float* mu = take(512); const float* va = take(512);
+        fold_weights_kernel<<<dim3(32, 16), tb, 0, st>>>(w, b, g, be, mu, va, eps, 1024, 512, net->w[4], net->bias[4]);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    {   // heads: pi rows [0,nsq), v row nsq; no BN
+        const float* wp = take(512LL * nsq); const float* bp = take(nsq);
+        const float* wv = take(512); const float* bv = take(1);
+        fold_weights_kernel<<<dim3(16, (nsq + 31) / 32), tb, 0, st>>>(wp, bp, nullptr, nullptr, nullptr, nullptr, eps, 512, nsq,
+                                                                      net->w[5], net->bias[5]);
+        OZ_CUDA(cudaGetLastError());
+        fold_weights_kernel<<<dim3(16, 1), tb, 0, st>>>(wv, bv, nullptr, nullptr, nullptr, nullptr, eps, 512, 1,
+                                                        net->w[5] + (size_t)nsq * 512, net->bias[5] + nsq);
+        OZ_CUDA(cudaGetLastError());
+        e->launches += 2;
+    }
+    if (staged) OZ_CUDA(cudaFreeAsync(staged, st));
+    OZ_CUDA(cudaStreamSynchronize(st));
+    net->loaded = true;
+    return OZ_OK;
+}
+
+int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const int* count_dev, int max_count,
+                   float* pi_dev, float* logits_dev, float* v_dev) {
+    OzNet* net = e->net;
+    if (!net || !net->loaded) { oz_set_error("network weights have not been loaded (oz_net_load_weights)"); return OZ_ERR_STATE; }
+    cudaStream_t st = e->stream;
+    const int n = net->n, C = net->C, nsq = n * n;
+    if (max_count > net->Bmax) max_count = net->Bmax;
+    const bool tm = net->timing;
+    if (tm) cudaEventRecord(net->ev[0], st);
+    {
+        long long warps = (long long)max_count * nsq;
+        int blocks = (int)((warps + 7) / 8);
+        conv1_gather_kernel<<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, net->table1, net->act1);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    if (tm) cudaEventRecord(net->ev[1], st);
+    for (int li = 0; li < 6; ++li) {
+        OzLayer& Lr = net->layer[li];
+        GemmParams p = Lr.p;
+        p.count = count_dev;
+        p.max_count = max_count;
+        p.pi = pi_dev; p.logits = logits_dev; p.v = v_dev;
+        int tiles = ((max_count + p.nb - 1) / p.nb) * p.n_tiles;
+        int grid = tiles < net->sm_count ? tiles : net->sm_count;
+        if (grid < 1) grid = 1;
+        if (Lr.epi == EPI_RELU_BF16)
+            oz_gemm_kernel<256, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<256>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+        else
+            oz_gemm_kernel<128, EPI_HEADS><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+        if (tm) cudaEventRecord(net->ev[2 + li], st);
+    }
+    if (tm) {
+        cudaEventSynchronize(net->ev[7]);
+        for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&e->layer_ms[i], net->ev[i], net->ev[i + 1]);
+    }
+    return OZ_OK;
+}
+
+int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes) {
+    OzNet* net = e->net;
+    if (!net || !net->loaded) { oz_set_error("network not loaded"); return OZ_ERR_STATE; }
+    const int n = net->n, C = net->C, B = net->Bmax;
+    bf16* ptrs[6] = {net->act1, net->act2, net->act3, net->act4, net->f1, net->f2};
+    int64_t sizes[6] = {(int64_t)B * n * n * C, (int64_t)B * n * n * C, (int64_t)B * (n - 2) * (n - 2) * C,
+                        (int64_t)B * (n - 4) * (n - 4) * C, (int64_t)B * 1024, (int64_t)B * 512};
+    OZ_REQUIRE(layer >= 0 && layer < 6, "layer %d out of range", layer);
+    OZ_REQUIRE(bytes >= 0 && bytes <= sizes[layer] * 2, "bytes out of range");
+    OZ_CUDA(cudaMemcpyAsync(host, ptrs[layer], (size_t)bytes, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    return OZ_OK;
+}

@@ -1,0 +1,206 @@
+// oz_rules.cu — K1/K2/K3: one-thread-per-position bitboard rules kernels (sm_100a).
+//
+//   K1 rules_legal_kernel   get_player_valid_actions            Othello/__init__.py:208-214
+//   K2 rules_apply_kernel   flip_board_squares + play turn logic Othello/__init__.py:237-247,147-159
+//                           (== OthelloMCTS.get_next_state, othelo_mcts.py:43-49)
+//   K3 perft_playout_kernel RandomOthelloAgent loop, whole game in registers   agents.py:20-24,71-84
+//
+// All three are integer-ALU bound: a position is 16 bytes in and 8-32 bytes out; the per-ply work is
+// ~470 64-bit logical ops.  Coalesced 8-byte loads/stores, grid sized to fill 148 SMs.
+#include "oz_engine.cuh"
+
+using namespace ozbb;
+
+__global__ void __launch_bounds__(256) rules_legal_kernel(const u64* __restrict__ own, const u64* __restrict__ opp,
+                                                          u64* __restrict__ moves, long long n, u64 full) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        moves[i] = legal_moves(own[i], opp[i], full);
+}
+
+__global__ void __launch_bounds__(256)
+rules_apply_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ sq,
+                   u64* __restrict__ own_out, u64* __restrict__ opp_out, u32* __restrict__ flags,
+                   u64* __restrict__ next_legal, long long n, u64 full) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        u64 o = own[i], p = opp[i];
+        int s = sq[i];
+        u64 m = (s >= 0 && s < 64) ? (1ull << s) : 0ull;
+        u32 fl;
+        u64 nl = 0;
+        if (!(m & legal_moves(o, p, full))) {
+            fl = 0x80000000u;  // not a legal move: position returned unchanged
+        } else {
+            fl = play_move(m, &o, &p, full, &nl);
+        }
+        own_out[i] = o;
+        opp_out[i] = p;
+        flags[i] = fl;
+        if (next_legal) next_legal[i] = nl;
+    }
+}
+
+// One thread = one whole random game; nothing but the final position touches memory.
+__global__ void __launch_bounds__(256)
+perft_playout_kernel(int n, u64 full, u64 seed, u64 first_id, long long n_games, int max_moves,
+                     u64* __restrict__ black, u64* __restrict__ white, u32* __restrict__ info,
+                     unsigned char* __restrict__ moves) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < n_games; g += stride) {
+        u64 own, opp;
+        initial_position(n, &own, &opp);  // BLACK to move: own = black
+        u32 player = 0, plies = 0, passes = 0, finished = 0;
+        u64 base = sm64(seed ^ (first_id + (u64)g));
+        u64 legal = legal_moves(own, opp, full);
+        unsigned char* mv = moves ? moves + g * 64 : nullptr;
+        while (legal && (max_moves < 0 || (int)plies < max_moves)) {
+            u32 cnt = (u32)popc(legal);
+            u32 k = pick_index(sm64(base + (u64)plies), cnt);
+            int s = kth_set_bit(legal, (int)k);
+            if (mv && plies < 64) mv[plies] = (unsigned char)s;
+            u32 fl = play_move(1ull << s, &own, &opp, full, &legal);
+            ++plies;
+            if (fl & MOVE_SWAPPED) player ^= 1u;
+            if (fl & MOVE_PASSED) ++passes;
+            if (fl & MOVE_FINISHED) finished = 1;
+        }
+        if (mv)
+            for (u32 p = plies; p < 64; ++p) mv[p] = 0xFF;
+        black[g] = player ? opp : own;
+        white[g] = player ? own : opp;
+        // OthelloGame.play switches current_player before it detects the end (Othello/__init__.py:147-156),
+        // so a finished game reports the opponent of the last mover.
+        if (finished) player ^= 1u;
+        info[g] = plies | (player << 8) | (finished << 9) | (passes << 16);
+    }
+}
+
+static int grid_for(long long n, int block) {
+    long long b = (n + block - 1) / block;
+    long long cap = 148LL * 8 * 4;  // 148 SMs x 8 resident 256-thread CTAs, a few waves
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+static int check_board_size(int n) {
+    if (n != 4 && n != 6 && n != 8) {
+        oz_set_error("board_size must be 4, 6 or 8 (got %d)", n);
+        return OZ_ERR_INVALID;
+    }
+    return OZ_OK;
+}
+
+extern "C" int oz_rules_legal_moves_dev(int32_t board_size, const uint64_t* own, const uint64_t* opp,
+                                        uint64_t* moves, int64_t n, void* stream) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    if (n <= 0) return OZ_OK;
+    rules_legal_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)own, (const u64*)opp,
+                                                                            (u64*)moves, n, full_mask(board_size));
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+extern "C" int oz_rules_apply_dev(int32_t board_size, const uint64_t* own, const uint64_t* opp, const int32_t* sq,
+                                  uint64_t* own_out, uint64_t* opp_out, uint32_t* flags, uint64_t* next_legal,
+                                  int64_t n, void* stream) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    if (n <= 0) return OZ_OK;
+    rules_apply_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)own, (const u64*)opp, sq, (u64*)own_out, (u64*)opp_out, flags, (u64*)next_legal, n,
+        full_mask(board_size));
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+extern "C" int oz_perft_playouts_dev(int32_t board_size, uint64_t seed, uint64_t first_game_id, int64_t n_games,
+                                     int32_t max_moves, uint64_t* black, uint64_t* white, uint32_t* info,
+                                     uint8_t* moves, void* stream) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    if (n_games <= 0) return OZ_OK;
+    // 128-thread CTAs: games end at different plies, smaller CTAs retire sooner (less tail per SM).
+    long long blocks = (n_games + 127) / 128;
+    long long cap = 148LL * 16 * 8;
+    if (blocks > cap) blocks = cap;
+    perft_playout_kernel<<<(int)blocks, 128, 0, (cudaStream_t)stream>>>(board_size, full_mask(board_size), seed,
+                                                                        first_game_id, n_games, max_moves,
+                                                                        (u64*)black, (u64*)white, info, moves);
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
+// ---- host-buffer entry points (copies inside) ---------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) { oz_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return OZ_ERR_NOMEM; }
+        return OZ_OK;
+    }
+};
+}  // namespace
+
+extern "C" int oz_rules_legal_moves_host(int32_t device, int32_t board_size, const uint64_t* own,
+                                         const uint64_t* opp, uint64_t* moves, int64_t n) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    OZ_REQUIRE(n >= 0 && (n == 0 || (own && opp && moves)), "null buffer");
+    if (n == 0) return OZ_OK;
+    OZ_CUDA(cudaSetDevice(device));
+    DevBuf a, b, c;
+    size_t bytes = (size_t)n * 8;
+    if (a.alloc(bytes) || b.alloc(bytes) || c.alloc(bytes)) return OZ_ERR_NOMEM;
+    OZ_CUDA(cudaMemcpy(a.p, own, bytes, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(b.p, opp, bytes, cudaMemcpyHostToDevice));
+    int rc = oz_rules_legal_moves_dev(board_size, (const uint64_t*)a.p, (const uint64_t*)b.p, (uint64_t*)c.p, n, nullptr);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpy(moves, c.p, bytes, cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+extern "C" int oz_rules_apply_host(int32_t device, int32_t board_size, const uint64_t* own, const uint64_t* opp,
+                                   const int32_t* sq, uint64_t* own_out, uint64_t* opp_out, uint32_t* flags,
+                                   uint64_t* next_legal, int64_t n) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    OZ_REQUIRE(n >= 0 && (n == 0 || (own && opp && sq && own_out && opp_out && flags)), "null buffer");
+    if (n == 0) return OZ_OK;
+    OZ_CUDA(cudaSetDevice(device));
+    DevBuf a, b, s, oa, ob, f, nl;
+    size_t b8 = (size_t)n * 8, b4 = (size_t)n * 4;
+    if (a.alloc(b8) || b.alloc(b8) || s.alloc(b4) || oa.alloc(b8) || ob.alloc(b8) || f.alloc(b4) || nl.alloc(b8))
+        return OZ_ERR_NOMEM;
+    OZ_CUDA(cudaMemcpy(a.p, own, b8, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(b.p, opp, b8, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(s.p, sq, b4, cudaMemcpyHostToDevice));
+    int rc = oz_rules_apply_dev(board_size, (const uint64_t*)a.p, (const uint64_t*)b.p, (const int32_t*)s.p,
+                                (uint64_t*)oa.p, (uint64_t*)ob.p, (uint32_t*)f.p, (uint64_t*)nl.p, n, nullptr);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpy(own_out, oa.p, b8, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(opp_out, ob.p, b8, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(flags, f.p, b4, cudaMemcpyDeviceToHost));
+    if (next_legal) OZ_CUDA(cudaMemcpy(next_legal, nl.p, b8, cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+extern "C" int oz_perft_playouts_host(int32_t device, int32_t board_size, uint64_t seed, uint64_t first_game_id,
+                                      int64_t n_games, int32_t max_moves, uint64_t* black, uint64_t* white,
+                                      uint32_t* info, uint8_t* moves) {
+    if (check_board_size(board_size)) return OZ_ERR_INVALID;
+    OZ_REQUIRE(n_games >= 0 && (n_games == 0 || (black && white && info)), "null buffer");
+    if (n_games == 0) return OZ_OK;
+    OZ_CUDA(cudaSetDevice(device));
+    DevBuf b, w, i, m;
+    size_t b8 = (size_t)n_games * 8, b4 = (size_t)n_games * 4;
+    if (b.alloc(b8) || w.alloc(b8) || i.alloc(b4)) return OZ_ERR_NOMEM;
+    if (moves && m.alloc((size_t)n_games * 64)) return OZ_ERR_NOMEM;
+    int rc = oz_perft_playouts_dev(board_size, seed, first_game_id, n_games, max_moves, (uint64_t*)b.p,
+                                   (uint64_t*)w.p, (uint32_t*)i.p, moves ? (uint8_t*)m.p : nullptr, nullptr);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpy(black, b.p, b8, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(white, w.p, b8, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(info, i.p, b4, cudaMemcpyDeviceToHost));
+    if (moves) OZ_CUDA(cudaMemcpy(moves, m.p, (size_t)n_games * 64, cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}

@@ -1,0 +1,674 @@
+// oz_tree.cu — K4/K5/K6/K11: batched PUCT search over hash-keyed node pools in HBM (sm_100a).
+//
+// One WARP owns one game (its node arena, its transposition table, its root) and runs that game's
+// simulations strictly one after another, exactly like the reference's recursive MCTS.simulate
+// (MCTS/__init__.py:30-71) — that is what makes visit counts bit-exact.  Throughput comes from
+// thousands of games (warps) in flight, not from parallelism inside a game.
+//
+//   select   lanes = children: coalesced loads of the node's P/Q/N rows, float64 UCB
+//            Q + c*P*sqrt(Ns)/(1+N) (MCTS/__init__.py:168-170), warp arg-max with the reference's
+//            first-max tie-break (:65)
+//   frontier first traversal of an edge: bitboard move + pass/terminal test (othelo_mcts.py:43-49,
+//            28-35), transposition lookup by exact board key (MCTS/__init__.py:42-44); the result
+//            (child node / terminal value) is cached on the edge so later descents are pointer chases
+//   expand   mask + normalise priors with numpy's pairwise np.sum order (MCTS/__init__.py:44-55,
+//            othelo_mcts.py:69-80); one network evaluation per node (othelo_mcts.py:82-88)
+//   backup   lanes = path entries; Q=(N*Q+v)/(N+1) with the reference's dynamic float32/float64 typing
+//            (MCTS/__init__.py:68-71), sign flip per ply
+//   move     visit counts -> action (first arg-max or epsilon-random), example record, OthelloGame.play
+//            (training.py:48-67)
+#include "oz_engine.cuh"
+
+using namespace ozbb;
+
+#define FULLW 0xffffffffu
+constexpr int TREE_WARPS = 4;  // warps (games) per CTA
+
+__device__ __forceinline__ OzNodeHdr* node_at(unsigned char* arena, u32 off) {
+    return (OzNodeHdr*)(arena + (size_t)off * 16);
+}
+__device__ __forceinline__ double* node_P(OzNodeHdr* h) { return (double*)((char*)h + sizeof(OzNodeHdr)); }
+__device__ __forceinline__ double* node_Q(OzNodeHdr* h, int k) { return node_P(h) + k; }
+__device__ __forceinline__ int* node_N(OzNodeHdr* h, int k) { return (int*)(node_P(h) + 2 * k); }
+__device__ __forceinline__ int* node_child(OzNodeHdr* h, int k) { return node_N(h, k) + k; }
+__host__ __device__ __forceinline__ u32 node_units(int k) { return (u32)((sizeof(OzNodeHdr) + 24 * k + 15) / 16); }
+
+__device__ __forceinline__ u64 key_hash(u64 own, u64 opp) {
+    u64 h = own * 0x9E3779B97F4A7C15ull ^ (opp + 0x632BE59BD9B4E019ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 32;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
+    return h;
+}
+
+// Warp-cooperative open-addressing lookup (32 slots per probe, one coalesced 256-byte load).
+// Returns node offset or -1; *ins = table slot where the key would be inserted.
+__device__ int table_find(const u64* __restrict__ table, int log2cap, unsigned char* arena, u64 own, u64 opp, int lane,
+                          u32* ins) {
+    u64 h = key_hash(own, opp);
+    u32 mask = (1u << log2cap) - 1u;
+    u32 fp = (u32)(h >> 32);
+    u32 start = (u32)h & mask;
+    for (u32 w = 0; w <= mask; w += 32) {
+        u32 idx = (start + w + (u32)lane) & mask;
+        u64 ent = table[idx];
+        unsigned empty = __ballot_sync(FULLW, ent == 0ull);
+        unsigned cand = __ballot_sync(FULLW, ent != 0ull && (u32)(ent >> 32) == fp);
+        if (empty) cand &= (1u << (__ffs(empty) - 1)) - 1u;
+        while (cand) {
+            int l = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            u32 off = __shfl_sync(FULLW, (u32)ent, l) - 1u;
+            OzNodeHdr* hd = node_at(arena, off);
+            if (hd->own == own && hd->opp == opp) return (int)off;
+        }
+        if (empty) {
+            *ins = (start + w + (u32)(__ffs(empty) - 1)) & mask;
+            return -1;
+        }
+    }
+    *ins = 0xffffffffu;
+    return -1;
+}
+
+// Per-warp registers that describe the simulation in flight.
+struct SimPath {
+    u32 n0, e0, n1, e1;  // lane l holds path entries l and l+32 : (node offset, child slot)
+};
+
+__device__ __forceinline__ void path_set(SimPath& p, int lane, int depth, u32 node, u32 edge) {
+    if (lane == (depth & 31)) {
+        if (depth < 32) { p.n0 = node; p.e0 = edge; }
+        else { p.n1 = node; p.e1 = edge; }
+    }
+}
+
+// MCTS/__init__.py:68-70 for every edge of the path, lanes in parallel (a path never repeats a node).
+// (is_int, iv, fv) = the value handed to the DEEPEST edge; it alternates sign going up (:71).
+__device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, int depth, bool is_int, int iv, float fv) {
+    for (int t = lane; t < depth; t += 32) {
+        u32 noff = (t < 32) ? p.n0 : p.n1;
+        u32 e = (t < 32) ? p.e0 : p.e1;
+        bool neg = ((depth - 1 - t) & 1) != 0;
+        int vi = neg ? -iv : iv;
+        float vf = neg ? -fv : fv;
+        OzNodeHdr* h = node_at(arena, noff);
+        int k = h->k;
+        double* Q = node_Q(h, k);
+        int* N = node_N(h, k);
+        int nn = N[e];
+        double q = Q[e];
+        u64 bit = 1ull << e;
+        bool f32 = (h->qf32 & bit) != 0ull;
+        if (nn == 0) {  // Q is python int 0
+            if (is_int) {
+                q = __ddiv_rn((double)(0 + vi), 1.0);
+            } else {
+                float s = __fadd_rn(0.0f, vf);
+                q = (double)__fdiv_rn(s, 1.0f);
+                f32 = true;
+            }
+        } else if (!f32) {  // python float
+            double t64 = __dmul_rn((double)nn, q);
+            if (is_int) {
+                q = __ddiv_rn(__dadd_rn(t64, (double)vi), (double)(nn + 1));
+            } else {
+                float s = __fadd_rn(__double2float_rn(t64), vf);
+                q = (double)__fdiv_rn(s, (float)(nn + 1));
+                f32 = true;
+            }
+        } else {  // numpy float32
+            float t32 = __fmul_rn((float)nn, (float)q);
+            float s = __fadd_rn(t32, is_int ? (float)vi : vf);
+            q = (double)__fdiv_rn(s, (float)(nn + 1));
+        }
+        Q[e] = q;
+        N[e] = nn + 1;
+        if (f32) h->qf32 |= bit;
+        h->ns += 1;
+    }
+    __syncwarp();
+}
+
+// Hash prior for one square / the value.
+__device__ __forceinline__ float hash_pi(u64 key, int sq) {
+    return (float)((double)((sm64(key + (u64)sq) >> 48) + 1ull) / 65536.0);
+}
+__device__ __forceinline__ float hash_v(u64 key) {
+    return (float)(((double)(sm64(key ^ 0xABCDEFull) >> 48) - 32768.0) / 32768.0);
+}
+
+struct Pending {
+    u64 own, opp, legal;
+    int parent, pedge, depth;
+};
+
+// Expansion (MCTS/__init__.py:44-57) of `pd` with this lane's priors (pi_lo: square `lane`, pi_hi: square
+// lane+32), followed by the backup of -v.  Returns false when the node pool is exhausted.
+__device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, unsigned char* arena, u64* table,
+                                  const Pending& pd, float pi_lo, float pi_hi, float v, double* sa,
+                                  const SimPath& path) {
+    const int n = P.n, nsq = P.nsq;
+    int k = popc(pd.legal);
+    u32 units = node_units(k);
+    u32 off = P.bump[slot];
+    u32 ins;
+    int found = table_find(table, P.table_log2, arena, pd.own, pd.opp, lane, &ins);
+    (void)found;
+    if (((u64)off + units) * 16ull > P.arena_stride || ins == 0xffffffffu) return false;
+
+    // numpy order: a = pi(f32) * mask(f64) over the flat (N,N) array (othelo_mcts.py:69-73)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int sq = lane + 32 * half;
+        int r = sq >> 3, c = sq & 7;
+        if (r < n && c < n) {
+            float pv = half ? pi_hi : pi_lo;
+            sa[r * n + c] = ((pd.legal >> sq) & 1ull) ? (double)pv : 0.0;
+        }
+    }
+    __syncwarp();
+    // np.sum pairwise (8 strided accumulators, then a fixed tree, then the tail)
+    int body = nsq - (nsq % 8);
+    double acc = 0.0;
+    if (lane < 8) {
+        acc = sa[lane];
+        for (int i = 8; i < body; i += 8) acc = __dadd_rn(acc, sa[i + lane]);
+    }
+    double r0 = __shfl_sync(FULLW, acc, 0), r1 = __shfl_sync(FULLW, acc, 1), r2 = __shfl_sync(FULLW, acc, 2),
+           r3 = __shfl_sync(FULLW, acc, 3), r4 = __shfl_sync(FULLW, acc, 4), r5 = __shfl_sync(FULLW, acc, 5),
+           r6 = __shfl_sync(FULLW, acc, 6), r7 = __shfl_sync(FULLW, acc, 7);
+    double sum = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    for (int i = body; i < nsq; ++i) sum = __dadd_rn(sum, sa[i]);
+
+    OzNodeHdr* h = node_at(arena, off);
+    double* Pp = node_P(h);
+    double* Qp = node_Q(h, k);
+    int* Np = node_N(h, k);
+    int* Cp = node_child(h, k);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        int sq = lane + 32 * half;
+        if ((pd.legal >> sq) & 1ull) {
+            int j = popc(pd.legal & ((1ull << sq) - 1ull));
+            int r = sq >> 3, c = sq & 7;
+            double pr = (sum > 0.0) ? __ddiv_rn(sa[r * n + c], sum) : __ddiv_rn(1.0, (double)k);
+            Pp[j] = pr;
+            Qp[j] = 0.0;
+            Np[j] = 0;
+            Cp[j] = OZ_CH_UNKNOWN;
+        }
+    }
+    if (lane == 0) {
+        h->own = pd.own; h->opp = pd.opp; h->legal = pd.legal; h->qf32 = 0ull;
+        h->ns = 0; h->k = k; h->pad0 = 0; h->pad1 = 0;
+        table[ins] = ((u64)(u32)(key_hash(pd.own, pd.opp) >> 32) << 32) | (u64)(off + 1u);
+        P.bump[slot] = off + units;
+        if (pd.parent >= 0) {
+            OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
+            node_child(ph, ph->k)[pd.pedge] = (int)off;
+        } else {
+            P.root_node[slot] = (int)off;
+        }
+    }
+    __syncwarp();
+    backup_path(arena, path, lane, pd.depth, false, 0, -v);  // MCTS:57 returns -v to the parent
+    return true;
+}
+
+__device__ __forceinline__ void warp_argmax(double& u, int& j) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        double ou = __shfl_xor_sync(FULLW, u, s);
+        int oj = __shfl_xor_sync(FULLW, j, s);
+        if (ou > u || (ou == u && oj < j)) { u = ou; j = oj; }
+    }
+}
+
+// The engine step.  Every warp: (1) finishes the simulation that was waiting for its leaf, (2) keeps
+// simulating until it needs another network evaluation or runs out of work.
+__global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTreeParams P) {
+    __shared__ double s_a[TREE_WARPS][64];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int slot = blockIdx.x * TREE_WARPS + wib;
+    if (slot >= P.G) return;
+    double* sa = s_a[wib];
+
+    int status = P.status[slot];
+    if (status != OZ_GAME_ACTIVE && status != OZ_GAME_WAIT_LEAF) return;
+
+    unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
+    u64* table = P.table + ((size_t)slot << P.table_log2);
+    const int n = P.n;
+    int sims_left = P.sims_left[slot];
+    u64 c_sims = 0, c_nodes = 0, c_term = 0, c_trans = 0, c_moves = 0;
+    int c_depth = 0;
+    SimPath path{0, 0, 0, 0};
+    Pending pd;
+
+    if (status == OZ_GAME_WAIT_LEAF) {
+        pd.own = P.pend_own[slot]; pd.opp = P.pend_opp[slot]; pd.legal = P.pend_legal[slot];
+        pd.parent = P.pend_parent[slot]; pd.pedge = P.pend_edge[slot]; pd.depth = P.pend_depth[slot];
+        int li = P.pend_leaf[slot];
+        const u32* pn = P.path_node + (size_t)slot * OZ_MAX_DEPTH;
+        const u32* pe = P.path_edge + (size_t)slot * OZ_MAX_DEPTH;
+        if (lane < pd.depth) { path.n0 = pn[lane]; path.e0 = pe[lane]; }
+        if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
+        // priors for this lane's two squares, row layout r*n+c with row stride 64
+        float pi_lo = 0.f, pi_hi = 0.f;
+        {
+            int r = lane >> 3, c = lane & 7;
+            if (r < n && c < n) pi_lo = P.leaf_pi[(size_t)li * 64 + r * n + c];
+            r += 4;
+            if (r < n && c < n) pi_hi = P.leaf_pi[(size_t)li * 64 + r * n + c];
+        }
+        float v = P.leaf_v[li];
+        if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
+            if (lane == 0) P.status[slot] = OZ_GAME_POOL_FULL;
+            return;
+        }
+        ++c_nodes; ++c_sims;
+        --sims_left;
+        status = OZ_GAME_ACTIVE;
+    }
+
+    u64 black = P.black[slot], white = P.white[slot];
+    int player = P.player[slot];
+    int ply = P.ply[slot];
+
+    while (true) {
+        if (sims_left <= 0) {
+            if (!P.selfplay) { status = OZ_GAME_IDLE; break; }
+            // ---- move transition: training.py:45-67 --------------------------------------------------
+            u64 own = player ? white : black, opp = player ? black : white;
+            int root = P.root_node[slot];
+            OzNodeHdr* h = node_at(arena, (u32)root);  // num_sims >= 2 guarantees the root exists
+            u64 legal = h->legal;
+            int k = h->k;
+            const int* Np = node_N(h, k);
+            // visit counts by child slot; first arg-max == np.argwhere(policy == policy.max())[0]
+            double best = -1.0; int bj = 1 << 20;
+            for (int j = lane; j < k; j += 32) {
+                double cnt = (double)Np[j];
+                if (cnt > best) { best = cnt; bj = j; }
+            }
+            warp_argmax(best, bj);
+            u64 base = sm64(P.seed ^ P.game_id[slot] ^ 0x5EEDC01Dull);
+            double coin = (double)(sm64(base + 2ull * (u64)ply) >> 11) * (1.0 / 9007199254740992.0);
+            int aj = bj;
+            if (!(coin <= P.e_greedy)) aj = (int)pick_index(sm64(base + 2ull * (u64)ply + 1ull), (u32)k);
+            int sq = kth_set_bit(legal, aj);
+            if (ply < 64) {
+                size_t ri = (size_t)slot * 64 + ply;
+                if (lane == 0) {
+                    P.rec_black[ri] = black; P.rec_white[ri] = white;
+                    P.rec_action[ri] = (unsigned char)sq; P.rec_player[ri] = (unsigned char)player;
+                }
+                if (P.log_visits) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        int s = lane + 32 * half;
+                        int cnt = ((legal >> s) & 1ull) ? Np[popc(legal & ((1ull << s) - 1ull))] : 0;
+                        P.rec_visits[ri * 64 + s] = cnt;
+                    }
+                }
+            }
+            u64 nl;
+            unsigned fl = play_move(1ull << sq, &own, &opp, P.full, &nl);
+            if (fl & MOVE_SWAPPED) player ^= 1;
+            black = player ? opp : own;
+            white = player ? own : opp;
+            ++ply; ++c_moves;
+            if (fl & MOVE_FINISHED) {
+                status = OZ_GAME_FINISHED;
+                if (lane == 0) {
+                    P.winner[slot] = (popc(black) >= popc(white)) ? 0 : 1;
+                    atomicSub(P.n_active, 1);
+                }
+                break;
+            }
+            u32 ins;
+            int nr = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+            if (lane == 0) P.root_node[slot] = nr;
+            __syncwarp();
+            if (P.max_moves >= 0 && ply >= P.max_moves) {
+                status = OZ_GAME_FINISHED;
+                if (lane == 0) { P.winner[slot] = -1; atomicSub(P.n_active, 1); }
+                break;
+            }
+            sims_left = P.num_sims;
+            continue;
+        }
+
+        // ---- one simulation: MCTS.simulate from the canonical root (othelo_mcts.py:22-26) -----------
+        int node = P.root_node[slot];
+        int depth = 0;
+        int outcome = 0;  // 1 = terminal, 2 = leaf
+        int term_val = 0;
+        if (node < 0) {
+            pd.own = player ? white : black;
+            pd.opp = player ? black : white;
+            pd.legal = legal_moves(pd.own, pd.opp, P.full);
+            pd.parent = -1; pd.pedge = 0; pd.depth = 0;
+            outcome = 2;
+            if (!pd.legal) {  // caller handed us a root whose side to move cannot move: nothing to simulate
+                status = P.selfplay ? OZ_GAME_FINISHED : OZ_GAME_IDLE;
+                if (P.selfplay && lane == 0) atomicSub(P.n_active, 1);
+                sims_left = 0;
+                break;
+            }
+        }
+        while (!outcome) {
+            OzNodeHdr* h = node_at(arena, (u32)node);
+            const int k = h->k;
+            const int ns = h->ns;
+            const double* Pp = node_P(h);
+            const double* Qp = node_Q(h, k);
+            const int* Np = node_N(h, k);
+            int* Cp = node_child(h, k);
+            const double sq_ns = __dsqrt_rn((double)ns);
+            double bu = -1.0e300; int bj = 1 << 20;
+            for (int j = lane; j < k; j += 32) {
+                double bound = __ddiv_rn(sq_ns, (double)(1 + Np[j]));
+                double u = __dadd_rn(Qp[j], __dmul_rn(__dmul_rn(P.c, Pp[j]), bound));
+                if (u > bu) { bu = u; bj = j; }
+            }
+            warp_argmax(bu, bj);
+            path_set(path, lane, depth, (u32)node, (u32)bj);
+            ++depth;
+            int ch = Cp[bj];
+            if (ch >= 0) { node = ch; continue; }
+            if (ch == OZ_CH_TERM_NEG || ch == OZ_CH_TERM_POS) {
+                term_val = (ch == OZ_CH_TERM_POS) ? 1 : -1;
+                outcome = 1;
+                break;
+            }
+            // frontier: get_next_state (othelo_mcts.py:43-49)
+            u64 own = h->own, opp = h->opp;
+            int sq = kth_set_bit(h->legal, bj);
+            u64 nl;
+            unsigned fl = play_move(1ull << sq, &own, &opp, P.full, &nl);
+            if (fl & MOVE_FINISHED) {
+                // is_terminal_state -> return -reward; reward = +1 iff ch0 count >= ch1 count (draw -> BLACK)
+                int reward = (popc(own) >= popc(opp)) ? 1 : -1;
+                term_val = -reward;
+                if (lane == 0) Cp[bj] = (term_val > 0) ? OZ_CH_TERM_POS : OZ_CH_TERM_NEG;
+                outcome = 1;
+                break;
+            }
+            u32 ins;
+            int found = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+            if (found >= 0) {  // transposition: the state already has a node
+                if (lane == 0) Cp[bj] = found;
+                ++c_trans;
+                node = found;
+                continue;
+            }
+            pd.own = own; pd.opp = opp; pd.legal = nl;
+            pd.parent = node; pd.pedge = bj; pd.depth = depth;
+            outcome = 2;
+        }
+        if (depth > c_depth) c_depth = depth;
+        __syncwarp();
+
+        if (outcome == 1) {
+            backup_path(arena, path, lane, depth, true, term_val, (float)term_val);
+            ++c_term; ++c_sims;
+            --sims_left;
+            continue;
+        }
+        // leaf
+        if (P.prior_mode == OZ_PRIOR_HASH) {
+            u64 key = sm64(pd.own ^ sm64(pd.opp));
+            float pi_lo = hash_pi(key, lane), pi_hi = hash_pi(key, lane + 32);
+            float v = hash_v(key);
+            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
+                status = OZ_GAME_POOL_FULL;
+                break;
+            }
+            ++c_nodes; ++c_sims;
+            --sims_left;
+            continue;
+        }
+        // hand the leaf to the evaluator and park this game
+        int li = 0;
+        if (lane == 0) li = atomicAdd(P.leaf_count, 1);
+        li = __shfl_sync(FULLW, li, 0);
+        if (lane == 0) {
+            P.leaf_own[li] = pd.own; P.leaf_opp[li] = pd.opp;
+            P.pend_own[slot] = pd.own; P.pend_opp[slot] = pd.opp; P.pend_legal[slot] = pd.legal;
+            P.pend_parent[slot] = pd.parent; P.pend_edge[slot] = pd.pedge; P.pend_depth[slot] = pd.depth;
+            P.pend_leaf[slot] = li;
+        }
+        u32* pn = P.path_node + (size_t)slot * OZ_MAX_DEPTH;
+        u32* pe = P.path_edge + (size_t)slot * OZ_MAX_DEPTH;
+        if (lane < pd.depth) { pn[lane] = path.n0; pe[lane] = path.e0; }
+        if (lane + 32 < pd.depth) { pn[lane + 32] = path.n1; pe[lane + 32] = path.e1; }
+        status = OZ_GAME_WAIT_LEAF;
+        break;
+    }
+
+    if (lane == 0) {
+        P.status[slot] = status;
+        P.sims_left[slot] = sims_left;
+        P.black[slot] = black; P.white[slot] = white; P.player[slot] = player; P.ply[slot] = ply;
+        if (c_sims) atomicAdd(&P.counters[0], c_sims);
+        if (c_nodes) atomicAdd(&P.counters[1], c_nodes);
+        if (c_term) atomicAdd(&P.counters[2], c_term);
+        if (c_trans) atomicAdd(&P.counters[6], c_trans);
+        if (c_moves) atomicAdd(&P.counters[7], c_moves);
+        atomicMax(&P.counters[5], (u64)c_depth);
+    }
+}
+
+// MCTS.N(root, action) for every game (MCTS/__init__.py:73-84).
+__global__ void tree_visits_kernel(const OzTreeParams P, int* __restrict__ visits, int* __restrict__ ns) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= P.G) return;
+    unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
+    const u64* table = P.table + ((size_t)slot << P.table_log2);
+    int player = P.player[slot];
+    u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
+    u32 ins;
+    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    int v0 = 0, v1 = 0, nsv = 0;
+    if (root >= 0) {
+        OzNodeHdr* h = node_at(arena, (u32)root);
+        u64 legal = h->legal;
+        const int* Np = node_N(h, h->k);
+        if ((legal >> lane) & 1ull) v0 = Np[popc(legal & ((1ull << lane) - 1ull))];
+        if ((legal >> (lane + 32)) & 1ull) v1 = Np[popc(legal & ((1ull << (lane + 32)) - 1ull))];
+        nsv = h->ns;
+    }
+    visits[(size_t)slot * 64 + lane] = v0;
+    visits[(size_t)slot * 64 + lane + 32] = v1;
+    if (lane == 0) ns[slot] = nsv;
+}
+
+__global__ void tree_root_stats_kernel(const OzTreeParams P, int slot, double* __restrict__ q, double* __restrict__ p,
+                                       int* __restrict__ tag, int* __restrict__ found) {
+    const int lane = threadIdx.x & 31;
+    unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
+    const u64* table = P.table + ((size_t)slot << P.table_log2);
+    int player = P.player[slot];
+    u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
+    u32 ins;
+    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    if (lane == 0) *found = root;
+    for (int half = 0; half < 2; ++half) {
+        int s = lane + 32 * half;
+        double qq = 0.0, pp = 0.0;
+        int tt = -1;
+        if (root >= 0) {
+            OzNodeHdr* h = node_at(arena, (u32)root);
+            if ((h->legal >> s) & 1ull) {
+                int j = popc(h->legal & ((1ull << s) - 1ull));
+                int k = h->k;
+                qq = node_Q(h, k)[j];
+                pp = node_P(h)[j];
+                int nn = node_N(h, k)[j];
+                tt = (nn == 0) ? 0 : (((h->qf32 >> j) & 1ull) ? 2 : 1);
+            }
+        }
+        q[s] = qq; p[s] = pp; tag[s] = tt;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+int oz_tree_alloc(oz_engine* e) {
+    const int G = e->cfg.max_games;
+    OzTreeParams& P = e->tp;
+    P.n = e->cfg.board_size;
+    P.nsq = P.n * P.n;
+    P.full = full_mask(P.n);
+    P.prior_mode = e->cfg.prior_mode;
+    P.log_visits = e->cfg.log_visits;
+    P.c = e->cfg.c_puct;
+    P.seed = e->cfg.seed;
+    int log2 = 6;
+    while ((1ll << log2) < 2ll * e->cfg.nodes_per_game) ++log2;
+    e->table_log2 = log2;
+    P.table_log2 = log2;
+    // average node: 48 + 24*k bytes; k averages ~8.4 (8x8), allow 12 and never less than one max-size node
+    u64 stride = (u64)e->cfg.nodes_per_game * (48 + 24 * 12);
+    if (stride < 4096) stride = 4096;
+    stride = (stride + 255) & ~255ull;
+    e->arena_stride = stride;
+    P.arena_stride = stride;
+    int rc = 0;
+#define A(field, T, count) if ((rc = oz_dev_alloc<T>(e, (T**)&P.field, (size_t)(count)))) return rc;
+    A(black, u64, G) A(white, u64, G) A(player, int, G) A(status, int, G) A(root_node, int, G)
+    A(sims_left, int, G) A(ply, int, G) A(game_id, u64, G) A(winner, int, G)
+    A(pend_own, u64, G) A(pend_opp, u64, G) A(pend_legal, u64, G) A(pend_parent, int, G) A(pend_edge, int, G)
+    A(pend_depth, int, G) A(pend_leaf, int, G)
+    A(path_node, u32, (size_t)G * OZ_MAX_DEPTH) A(path_edge, u32, (size_t)G * OZ_MAX_DEPTH)
+    A(arena, unsigned char, (size_t)G * stride) A(bump, u32, G) A(table, u64, (size_t)G << log2)
+    A(leaf_own, u64, G) A(leaf_opp, u64, G) A(leaf_count, int, 4)
+    A(rec_black, u64, (size_t)G * 64) A(rec_white, u64, (size_t)G * 64) A(rec_action, unsigned char, (size_t)G * 64)
+    A(rec_player, unsigned char, (size_t)G * 64)
+    A(counters, u64, 8) A(n_active, int, 4)
+    if (e->cfg.log_visits) { A(rec_visits, int, (size_t)G * 64 * 64) } else { P.rec_visits = nullptr; }
+#undef A
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_pi, (size_t)G * 64))) return rc;
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_logits, (size_t)G * 64))) return rc;
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_v, (size_t)G))) return rc;
+    P.leaf_pi = e->leaf_pi;
+    P.leaf_v = e->leaf_v;
+    OZ_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(u64), e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.status, 0, G * sizeof(int), e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, 4 * sizeof(int), e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.n_active, 0, 4 * sizeof(int), e->stream));
+    return OZ_OK;
+}
+
+__global__ void tree_init_slots_kernel(const OzTreeParams P, int n_games, const u64* __restrict__ black,
+                                       const u64* __restrict__ white, const int* __restrict__ player,
+                                       const u64* __restrict__ ids, int clear) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= P.G) return;
+    if (g < n_games) {
+        u64 b, w;
+        if (black) { b = black[g]; w = white[g]; }
+        else initial_position(P.n, &b, &w);
+        P.black[g] = b; P.white[g] = w;
+        P.player[g] = player ? player[g] : 0;
+        if (clear) {
+            P.game_id[g] = ids ? ids[g] : (u64)g;
+            P.bump[g] = 1;  // offset 0 is never a node, so (off+1) != 0 and child >= 0 stays unambiguous
+            P.ply[g] = 0;
+            P.winner[g] = -1;
+        }
+        P.status[g] = OZ_GAME_IDLE;
+        P.root_node[g] = -1;
+        P.sims_left[g] = 0;
+    } else if (clear) {
+        P.status[g] = OZ_GAME_IDLE;
+        P.sims_left[g] = 0;
+    }
+}
+
+// Re-resolve roots through the transposition table (after set_roots on a live tree).
+__global__ void tree_find_roots_kernel(const OzTreeParams P) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= P.G) return;
+    unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
+    const u64* table = P.table + ((size_t)slot << P.table_log2);
+    int player = P.player[slot];
+    u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
+    u32 ins;
+    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    if (lane == 0) P.root_node[slot] = root;
+}
+
+int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white, const int* player, const u64* ids,
+                  bool clear) {
+    OzTreeParams& P = e->tp;
+    const int G = e->cfg.max_games;
+    OZ_REQUIRE(n_games >= 1 && n_games <= G, "n_games %d out of range (max_games %d)", n_games, G);
+    OZ_REQUIRE((black == nullptr) == (white == nullptr), "black/white must both be given or both NULL");
+    u64 *d_b = nullptr, *d_w = nullptr, *d_id = nullptr;
+    int* d_p = nullptr;
+    // staging buffers live in the (not yet used) leaf arrays' neighbours: allocate temporaries
+    size_t b8 = (size_t)n_games * 8, b4 = (size_t)n_games * 4;
+    if (black) {
+        OZ_CUDA(cudaMallocAsync((void**)&d_b, b8, e->stream));
+        OZ_CUDA(cudaMallocAsync((void**)&d_w, b8, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(d_b, black, b8, cudaMemcpyHostToDevice, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(d_w, white, b8, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (player) {
+        OZ_CUDA(cudaMallocAsync((void**)&d_p, b4, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(d_p, player, b4, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (ids) {
+        OZ_CUDA(cudaMallocAsync((void**)&d_id, b8, e->stream));
+        OZ_CUDA(cudaMemcpyAsync(d_id, ids, b8, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (clear) {
+        OZ_CUDA(cudaMemsetAsync(P.table, 0, ((size_t)n_games << P.table_log2) * sizeof(u64), e->stream));
+        OZ_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(u64), e->stream));
+        OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
+    }
+    P.G = n_games;
+    tree_init_slots_kernel<<<(G + 255) / 256, 256, 0, e->stream>>>(P, n_games, d_b, d_w, d_p, d_id, clear ? 1 : 0);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    if (!clear) {
+        tree_find_roots_kernel<<<(n_games + 3) / 4, 128, 0, e->stream>>>(P);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+    }
+    if (d_b) { cudaFreeAsync(d_b, e->stream); cudaFreeAsync(d_w, e->stream); }
+    if (d_p) cudaFreeAsync(d_p, e->stream);
+    if (d_id) cudaFreeAsync(d_id, e->stream);
+    e->n_games = n_games;
+    return OZ_OK;
+}
+
+int oz_tree_step(oz_engine* e) {
+    OzTreeParams& P = e->tp;
+    int blocks = (P.G + TREE_WARPS - 1) / TREE_WARPS;
+    tree_step_kernel<<<blocks, TREE_WARPS * 32, 0, e->stream>>>(P);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    return OZ_OK;
+}
+
+int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev) {
+    OzTreeParams& P = e->tp;
+    tree_visits_kernel<<<(P.G + 3) / 4, 128, 0, e->stream>>>(P, visits_dev, ns_dev);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    return OZ_OK;
+}
+
+int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev) {
+    OzTreeParams& P = e->tp;
+    tree_root_stats_kernel<<<1, 32, 0, e->stream>>>(P, game, q_dev, p_dev, tag_dev, tag_dev + 64);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    return OZ_OK;
+}

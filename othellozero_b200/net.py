@@ -1,0 +1,163 @@
+"""Network side of the drop-in: the NNetWrapper contract (Net/NNet.py:22-101) over the bf16 tcgen05
+OthelloNNet tower in liboz_b200.so.
+
+Weights travel as ONE float32 blob in Keras ``model.get_weights()`` order for the graph of
+Net/OthelloNN.py:42-52 (kernel HWIO / Dense (in,out), bias, then BN gamma, beta, moving_mean,
+moving_variance after each of the six conv/dense blocks, then the two heads).
+"""
+from __future__ import annotations
+
+import enum
+
+import numpy as np
+
+from . import engine as _engine
+from ._lib import PRIOR_NET
+
+
+class NeuralNets(enum.Enum):
+    """Net/NNet.py:14-16."""
+    ONN = enum.auto()
+    BNN = enum.auto()
+
+
+def blob_layout(board_size: int, channels: int = 512):
+    """[(name, shape)] in blob order."""
+    n, C = board_size, channels
+    k1 = (n - 4) * (n - 4) * C
+    L = []
+
+    def bn(prefix, c):
+        L.extend([(f"{prefix}.gamma", (c,)), (f"{prefix}.beta", (c,)), (f"{prefix}.mean", (c,)), (f"{prefix}.var", (c,))])
+
+    L += [("conv1.kernel", (3, 3, 2, C)), ("conv1.bias", (C,))]
+    bn("bn1", C)
+    for i in (2, 3, 4):
+        L += [(f"conv{i}.kernel", (3, 3, C, C)), (f"conv{i}.bias", (C,))]
+        bn(f"bn{i}", C)
+    L += [("fc1.kernel", (k1, 1024)), ("fc1.bias", (1024,))]
+    bn("bn5", 1024)
+    L += [("fc2.kernel", (1024, 512)), ("fc2.bias", (512,))]
+    bn("bn6", 512)
+    L += [("pi.kernel", (512, n * n)), ("pi.bias", (n * n,)), ("v.kernel", (512, 1)), ("v.bias", (1,))]
+    return L
+
+
+def blob_size(board_size: int, channels: int = 512) -> int:
+    return int(sum(int(np.prod(s)) for _, s in blob_layout(board_size, channels)))
+
+
+def unpack_blob(blob: np.ndarray, board_size: int, channels: int = 512) -> dict:
+    out, off = {}, 0
+    for name, shape in blob_layout(board_size, channels):
+        cnt = int(np.prod(shape))
+        out[name] = blob[off:off + cnt].reshape(shape)
+        off += cnt
+    assert off == blob.size, "blob size mismatch"
+    return out
+
+
+def pack_blob(weights: dict, board_size: int, channels: int = 512) -> np.ndarray:
+    return np.concatenate([np.asarray(weights[name], dtype=np.float32).reshape(-1)
+                           for name, _ in blob_layout(board_size, channels)])
+
+
+def init_weights(board_size: int, channels: int = 512, seed: int = 0, randomize_bn: bool = False) -> np.ndarray:
+    """Keras defaults: glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1.
+    randomize_bn=True perturbs BN statistics / biases so that folding is exercised by the tests."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, shape in blob_layout(board_size, channels):
+        kind = name.split(".")[1]
+        if kind == "kernel":
+            if len(shape) == 4:
+                fan_in, fan_out = shape[0] * shape[1] * shape[2], shape[0] * shape[1] * shape[3]
+            else:
+                fan_in, fan_out = shape
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            w[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+        elif kind in ("bias", "beta", "mean"):
+            w[name] = (rng.normal(0, 0.1, size=shape) if randomize_bn else np.zeros(shape)).astype(np.float32)
+        elif kind == "gamma":
+            w[name] = (rng.uniform(0.5, 1.5, size=shape) if randomize_bn else np.ones(shape)).astype(np.float32)
+        elif kind == "var":
+            w[name] = (rng.uniform(0.5, 2.0, size=shape) if randomize_bn else np.ones(shape)).astype(np.float32)
+    return pack_blob(w, board_size, channels)
+
+
+def boards_to_bits(boards) -> tuple[np.ndarray, np.ndarray]:
+    """(B,N,N,2) bool/0-1 array -> (ch0 bits, ch1 bits) uint64, bit r*8+c."""
+    b = np.asarray(boards).astype(bool)
+    if b.ndim == 3:
+        b = b[None]
+    B, n = b.shape[0], b.shape[1]
+    weights = np.zeros((n, n), dtype=np.uint64)
+    for r in range(n):
+        for c in range(n):
+            weights[r, c] = np.uint64(1) << np.uint64(r * 8 + c)
+    own = (b[..., 0] * weights).sum(axis=(1, 2), dtype=np.uint64)
+    opp = (b[..., 1] * weights).sum(axis=(1, 2), dtype=np.uint64)
+    return own, opp
+
+
+def bits_to_board(ch0: int, ch1: int, n: int) -> np.ndarray:
+    """-> (N,N,2) bool array in the reference's layout (Othello/__init__.py:22-25)."""
+    out = np.zeros((n, n, 2), dtype=bool)
+    for r in range(n):
+        for c in range(n):
+            out[r, c, 0] = (int(ch0) >> (r * 8 + c)) & 1
+            out[r, c, 1] = (int(ch1) >> (r * 8 + c)) & 1
+    return out
+
+
+class B200NNet:
+    """NNetWrapper stand-in (Net/NNet.py:22-101) whose predict runs on the B200 tower.
+
+    ``predict(board (N,N,2)) -> (pi (N,N) float32 probabilities, v float32)`` — Net/NNet.py:70-87.
+    ``train`` is not part of the self-play hot path and raises.
+    """
+
+    def __init__(self, board_size=(8, 8), num_channels_1: int = 512, network=NeuralNets.ONN, device: int = 0,
+                 max_batch: int = 4096, seed: int = 0, blob: np.ndarray | None = None):
+        if network is not NeuralNets.ONN:
+            raise TypeError("only NeuralNets.ONN is implemented on the B200 path (BNN is out of scope)")
+        self.board_size_x, self.board_size_y = board_size
+        assert self.board_size_x == self.board_size_y, "square boards only"
+        self.action_size = self.board_size_x * self.board_size_y
+        self.network_type = network
+        self.channels = num_channels_1
+        self.device = device
+        self.max_batch = max_batch
+        self.blob = blob if blob is not None else init_weights(self.board_size_x, num_channels_1, seed)
+        self._eng = _engine.Engine(self.board_size_x, max_games=max_batch, nodes_per_game=2, prior_mode=PRIOR_NET,
+                                   device=device)
+        self._eng.load_weights(self.blob, self.channels)
+
+    def set_weights(self, blob: np.ndarray):
+        self.blob = np.ascontiguousarray(blob, dtype=np.float32)
+        self._eng.load_weights(self.blob, self.channels)
+
+    def predict_batch(self, own, opp, want_logits: bool = False):
+        """Canonical bitboards -> (pi [B,N*N], v [B]) (+ logits)."""
+        pi, lg, v = self._eng.net_forward(own, opp, want_logits=want_logits)
+        return (pi, lg, v) if want_logits else (pi, v)
+
+    def predict(self, board):
+        own, opp = boards_to_bits(board)
+        pi, v = self.predict_batch(own, opp)
+        return pi[0].reshape(self.board_size_x, self.board_size_y), np.float32(v[0])
+
+    def train(self, examples, verbose=None):
+        raise NotImplementedError("training (Net/NNet.py:53-68) is outside the self-play hot path; see DESIGN.md")
+
+    def save_checkpoint(self, filepath):
+        np.savez(filepath, blob=self.blob, board_size=self.board_size_x, channels=self.channels)
+
+    def load_checkpoint(self, filepath):
+        d = np.load(filepath if str(filepath).endswith(".npz") else str(filepath) + ".npz")
+        assert int(d["board_size"]) == self.board_size_x and int(d["channels"]) == self.channels
+        self.set_weights(d["blob"])
+
+    def copy(self):
+        return B200NNet((self.board_size_x, self.board_size_y), self.channels, self.network_type, self.device,
+                        self.max_batch, blob=self.blob.copy())

@@ -1,0 +1,124 @@
+"""K7-K10 (bf16 tcgen05 OthelloNNet tower) against the PyTorch fp32 restatement (oracle/net_torch.py).
+Tolerance (north_star): 1e-2 absolute on policy logits and on the value."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import net_torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _positions(n, count, seed):
+    """Canonical positions sampled from random playouts at assorted depths."""
+    own, opp = [], []
+    for g in range(count):
+        po = oracle.playout(n, seed, g, max_moves=g % (n * n - 6))
+        b, w, p = po["black"], po["white"], po["player"]
+        own.append(w if p else b)
+        opp.append(b if p else w)
+    return np.array(own, dtype=np.uint64), np.array(opp, dtype=np.uint64)
+
+
+def _check(n, C, B, max_games, seed, randomize_bn=True):
+    import torch
+    from othellozero_b200 import engine, net
+    blob = net.init_weights(n, C, seed=seed, randomize_bn=randomize_bn)
+    assert blob.size == net_torch.blob_floats(n, C)
+    e = engine.Engine(n, max_games=max_games, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+    e.load_weights(blob, C)
+    own, opp = _positions(n, B, seed)
+    pi, lg, v = e.net_forward(own, opp)
+    x = net_torch.boards_from_bits(own, opp, n)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    rpi, rlg, rv, hidden = net_torch.forward(blob, x, n, C, device=dev, return_hidden=True)
+    # layer-by-layer first: localises a failure
+    rows = [n * n, n * n, (n - 2) ** 2, (n - 4) ** 2, 1, 1]
+    chans = [C, C, C, C, 1024, 512]
+    for li in range(6):
+        got = e.activation(li, B, rows[li], chans[li])
+        ref = hidden[li]
+        scale = max(1.0, float(np.abs(ref).max()))
+        err = float(np.abs(got - ref).max())
+        assert err <= 0.03 * scale, f"layer {li}: max abs err {err} (scale {scale})"
+    assert np.abs(lg - rlg).max() <= TOL, f"logits err {np.abs(lg - rlg).max()}"
+    assert np.abs(v - rv).max() <= TOL, f"value err {np.abs(v - rv).max()}"
+    assert np.abs(pi - rpi).max() <= TOL
+    assert np.allclose(pi.sum(axis=1), 1.0, atol=1e-4)
+    e.close()
+    return lg, v
+
+
+def test_net_8x8_c512_ragged_batch():
+    # 301 boards: not a multiple of any tile's boards-per-tile (2, 3, 8, 128)
+    _check(8, 512, 301, 512, seed=1)
+
+
+def test_net_8x8_keras_default_init():
+    _check(8, 512, 64, 64, seed=2, randomize_bn=False)
+
+
+def test_net_6x6_c512():
+    _check(6, 512, 130, 256, seed=3)
+
+
+def test_net_small_channels_single_board():
+    _check(8, 128, 1, 8, seed=4)
+
+
+def test_net_is_row_independent():
+    """A board's output must not depend on its position in the batch or on its neighbours."""
+    from othellozero_b200 import engine, net
+    n, C = 8, 128
+    blob = net.init_weights(n, C, seed=5, randomize_bn=True)
+    e = engine.Engine(n, max_games=256, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+    e.load_weights(blob, C)
+    own, opp = _positions(n, 200, 9)
+    pi, lg, v = e.net_forward(own, opp)
+    perm = np.random.default_rng(0).permutation(200)
+    pi2, lg2, v2 = e.net_forward(own[perm], opp[perm])
+    assert np.array_equal(lg[perm], lg2) and np.array_equal(v[perm], v2)
+    pi3, lg3, v3 = e.net_forward(own[:7], opp[:7])
+    assert np.array_equal(lg[:7], lg3)
+    e.close()
+
+
+def test_predict_contract():
+    """NNetWrapper.predict: (N,N,2) board -> (pi (N,N) float32 probabilities, v float32)."""
+    from othellozero_b200 import net
+    nn = net.B200NNet((8, 8), num_channels_1=128, max_batch=8, seed=6)
+    board = oracle.initial_board(8).astype(bool)
+    pi, v = nn.predict(board)
+    assert pi.shape == (8, 8) and pi.dtype == np.float32 and abs(float(pi.sum()) - 1.0) < 1e-4
+    assert -1.0 <= float(v) <= 1.0
+    x = board[None].astype(np.float32)
+    rpi, _, rv = net_torch.forward(nn.blob, x, 8, 128)
+    assert np.abs(pi.ravel() - rpi[0]).max() <= TOL and abs(float(v) - float(rv[0])) <= TOL
+
+
+def test_selfplay_with_net_matches_oracle_search():
+    """End to end: device self-play with the device net == oracle search fed the SAME (device) priors."""
+    from othellozero_b200 import engine, net
+    n, C, sims = 6, 128, 16
+    blob = net.init_weights(n, C, seed=7, randomize_bn=True)
+    e = engine.Engine(n, max_games=4, nodes_per_game=sims * 40, prior_mode=engine.PRIOR_NET, log_visits=True)
+    e.load_weights(blob, C)
+    e.selfplay_begin(4, sims, 1.0, 1.0)
+    assert e.selfplay_run(-1) == 0
+    out = e.selfplay_records()
+    pe = engine.Engine(n, max_games=64, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+    pe.load_weights(blob, C)
+
+    def predict(board):
+        own, opp = net.boards_to_bits(board)
+        pi, _, v = pe.net_forward(own, opp, want_logits=False)
+        return pi[0].reshape(n, n), v[0]
+
+    ref = oracle.execute_episode(n, sims, predict=predict, log_visits=True)
+    k = int(out["n_moves"][0])
+    assert [int(a) for a in out["action"][0][:k]] == [(a // n) * 8 + a % n for a in ref["moves"]]
+    assert int(out["winner"][0]) == ref["winner"]
+    assert e.counters()["nodes"] == 4 * ref["net_calls"]
+    e.close(); pe.close()

@@ -1,0 +1,152 @@
+"""K4-K6/K11 (CUDA PUCT search + self-play driver) against the oracle and the reference's golden episodes.
+Visit counts, Q values (incl. their float32/float64 typing), moves and winners must be bit-exact."""
+import numpy as np
+import pytest
+
+import oracle
+import prior_fns
+from gpu_util import canon_board, sq8, visits_to_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    from othellozero_b200 import engine
+    return engine
+
+
+def test_root_visits_golden(E, golden_roots):
+    for rec in golden_roots:
+        n = rec["n"]
+        e = E.Engine(n, max_games=1, nodes_per_game=rec["sims"] + 8, prior_mode=E.PRIOR_HASH)
+        e.reset(1)
+        e.search(rec["sims"])
+        v, ns = e.visits()
+        assert int(ns[0]) == rec["ns"]
+        assert visits_to_grid(v[0], n).tolist() == rec["visits"]
+        assert e.counters()["nodes"] == rec["net_calls"]
+        e.close()
+
+
+def test_sims_one_at_a_time_equals_batch(E):
+    """OthelloMCTS.simulate is called once per simulation by the reference (training.py:42-43)."""
+    a = E.Engine(8, 1, 256, E.PRIOR_HASH)
+    b = E.Engine(8, 1, 256, E.PRIOR_HASH)
+    a.reset(1); b.reset(1)
+    a.search(60)
+    for _ in range(60):
+        b.search(1)
+    assert np.array_equal(a.visits()[0], b.visits()[0])
+    qa, pa, ta = a.root_stats(0)
+    qb, pb, tb = b.root_stats(0)
+    assert np.array_equal(qa, qb) and np.array_equal(pa, pb) and np.array_equal(ta, tb)
+
+
+@pytest.mark.parametrize("name", ["hash_4_40", "hash_6_25", "hash_6_60_c2", "hash_8_100"])
+def test_selfplay_hash_prior_golden(E, golden_episodes, name):
+    rec = golden_episodes[name]
+    n = rec["n"]
+    e = E.Engine(n, max_games=2, nodes_per_game=rec["sims"] * (n * n) + 64, prior_mode=E.PRIOR_HASH,
+                 c_puct=rec["c"], log_visits=True)
+    e.selfplay_begin(2, rec["sims"], temperature=rec["T"], e_greedy=1.0)
+    assert e.selfplay_run(-1) == 0
+    out = e.selfplay_records()
+    for g in range(2):  # both games are deterministic and identical
+        k = int(out["n_moves"][g])
+        assert [int(a) for a in out["action"][g][:k]] == [sq8(a, n) for a in rec["moves"]]
+        assert [int(p) for p in out["player"][g][:k]] == rec["players"]
+        assert int(out["winner"][g]) == rec["winner"]
+        for p in range(k):
+            assert visits_to_grid(out["visits"][g][p], n).tolist() == rec["visits"][p]
+    assert e.counters()["nodes"] == 2 * rec["net_calls"]
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["sha_4_30", "sha_6_25", "zero_6_10", "sha_8_50"])
+def test_host_prior_episode_golden(E, golden_episodes, name):
+    """Host-fed NON-dyadic float32 priors: numpy's pairwise-sum order and the float32 Q arithmetic."""
+    rec = golden_episodes[name]
+    n = rec["n"]
+    fn = prior_fns.sha_prior if name.startswith("sha") else prior_fns.zero_prior
+
+    def predict_batch(own, opp):
+        outs = [fn(canon_board(o, p, n)) for o, p in zip(own, opp)]
+        return np.stack([o[0].ravel() for o in outs]), np.array([o[1] for o in outs], dtype=np.float32)
+
+    e = E.Engine(n, max_games=1, nodes_per_game=rec["sims"] * (n * n) + 64, prior_mode=E.PRIOR_HOST, c_puct=rec["c"])
+    board = oracle.initial_board(n)
+    game = dict(board=board, player=0)
+    b, w = oracle.board_to_bits(board)
+    e.reset(1, [b], [w], [0])
+    moves = []
+    lib = oracle.lib()
+    import ctypes as C
+    g = np.zeros(1)  # placeholder to keep flake quiet
+    cur = oracle.as_board(board).copy()
+    player = 0
+    for p, exp_vis in enumerate(rec["visits"]):
+        e.search(rec["sims"], predict_batch)
+        v, ns = e.visits()
+        assert visits_to_grid(v[0], n).tolist() == exp_vis, f"move {p}"
+        a = rec["moves"][p]
+        moves.append(a)
+        # advance with the oracle's rules (OthelloGame.play)
+        nb = oracle.flip_board(cur, player, a // n, a % n)
+        nxt = 1 - player
+        if not oracle.valid_actions(nb, nxt):
+            nxt = player if oracle.valid_actions(nb, player) else nxt
+        cur, player = nb, nxt
+        if oracle.has_finished(cur):
+            break
+        b, w = oracle.board_to_bits(cur)
+        e.set_roots([b], [w], [player])
+    assert e.counters()["nodes"] == rec["net_calls"]
+    e.close()
+
+
+def test_q_values_and_types(E, golden_episodes):
+    for name in ("hash_4_40", "hash_6_25"):
+        rec = golden_episodes[name]
+        n = rec["n"]
+        e = E.Engine(n, 1, 4096, E.PRIOR_HASH, c_puct=rec["c"])
+        e.reset(1)
+        e.search(rec["sims"])
+        q, p, tag = e.root_stats(0)
+        for k, (val, typ) in rec["q"][0].items():
+            s = sq8(int(k), n)
+            assert q[s] == val
+            assert tag[s] == {"int": 0, "float": 1, "float32": 2}[typ]
+        e.close()
+
+
+def test_many_games_vs_oracle_with_random_moves(E):
+    """e_greedy < 1 with the engine RNG; distinct start positions; every game checked against the oracle."""
+    n, sims, G = 6, 20, 64
+    starts = [oracle.playout(n, 5, g, max_moves=g % 5) for g in range(G)]
+    black = [s["black"] for s in starts]
+    white = [s["white"] for s in starts]
+    player = [s["player"] for s in starts]
+    ids = [1000 + g for g in range(G)]
+    e = E.Engine(n, G, sims * 40 + 64, E.PRIOR_HASH, seed=42, log_visits=True)
+    e.selfplay_begin(G, sims, 1.0, 0.7, -1, black, white, player, ids)
+    assert e.selfplay_run(-1) == 0
+    out = e.selfplay_records()
+    for g in range(G):
+        ref = oracle.execute_episode(n, sims, e_greedy=0.7, seed=42, game_id=ids[g],
+                                     start_board=starts[g]["board"], start_player=player[g], log_visits=True)
+        k = int(out["n_moves"][g])
+        assert [int(a) for a in out["action"][g][:k]] == [sq8(a, n) for a in ref["moves"]], f"game {g}"
+        assert int(out["winner"][g]) == ref["winner"]
+        assert [int(x) for x in out["black"][g][:k]] == ref["black"]
+        for p in range(k):
+            assert visits_to_grid(out["visits"][g][p], n).tolist() == ref["visits"][p].tolist()
+    e.close()
+
+
+def test_pool_exhaustion_is_reported(E):
+    e = E.Engine(8, 1, 16, E.PRIOR_HASH)
+    e.selfplay_begin(1, 50)
+    with pytest.raises(MemoryError):
+        e.selfplay_run(-1)
+    e.close()
