@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — self-play hot path throughput on B200 (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload selfplay|perft|tree]
+
+Default workload = BASELINE.json configs[2]: 8x8 Othello self-play, 100 sims/move, 4096 concurrent games per GPU,
+random-init OthelloNNet (C=512) evaluated in bf16 on the tcgen05 tower.  One "step" = 100 engine steps (one tree
+kernel + one leaf-batch network evaluation each), i.e. >= 100 simulations — about one move — for every game.
+`value` = MCTS simulations / s with everything resident in HBM; `e2e` = complete self-play games through the
+public API with host buffers (start positions in, example records out).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_EVAL_8 = 566_428_672       # 2*MACs of OthelloNN(C=512) on one 8x8 position
+FLOP_CONV2_PER_BOARD_8 = 2 * 150_994_944
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (C restatement of the reference's search + PyTorch fp32 batch-1 net), one process
+# per host core, each playing the first moves of an 8x8 / 100-sim episode.
+# ------------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(n, C):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import net_torch
+    from othellozero_b200 import net as oznet  # weight init only (numpy); no CUDA is touched here
+    _W["net"] = net_torch.TorchNet(oznet.init_weights(n, C, seed=0), n, C)
+    _W["n"] = n
+
+
+def _cpu_worker(args):
+    wid, sims, moves, seed = args
+    import oracle
+    n = _W["n"]
+    start = oracle.playout(n, seed, wid, max_moves=wid % 8)
+    t0 = time.perf_counter()
+    out = oracle.execute_episode(n, sims, c=1.0, temperature=1.0, e_greedy=0.9, predict=_W["net"].predict, seed=seed,
+                                 game_id=wid, start_board=start["board"], start_player=start["player"],
+                                 max_moves=moves)
+    return out["sims"], len(out["moves"]), out["net_calls"], time.perf_counter() - t0
+
+
+class CpuArm:
+    """The oracle port on all host cores: one process per core, each playing the first move(s) of its own 8x8 episode
+    (sequential sims, one batch-1 fp32 net call per expanded node - the reference's structure)."""
+
+    def __init__(self, n=8, C=512, procs=None):
+        import multiprocessing as mp
+        cores = os.cpu_count() or 1
+        self.procs = procs or min(cores, 32)
+        self.pool = mp.get_context("spawn").Pool(self.procs, initializer=_cpu_init, initargs=(n, C))
+        self.calls = 0
+
+    def sample(self, sims=100, moves=1):
+        t0 = time.perf_counter()
+        base = self.calls * self.procs
+        res = self.pool.map(_cpu_worker, [(base + w, sims, moves, 0) for w in range(self.procs)])
+        self.calls += 1
+        wall = time.perf_counter() - t0
+        tot_sims = sum(r[0] for r in res)
+        return dict(value=tot_sims / wall, unit="sims/s", cores=self.procs, kind="port",
+                    sample=f"{self.procs} processes x {moves} move(s) x {sims} sims of 8x8 episodes: C oracle search + "
+                           f"PyTorch fp32 batch-1 net, 1 thread each; {tot_sims} sims, {sum(r[2] for r in res)} net calls "
+                           f"in {wall:.1f}s",
+                    moves_per_s=sum(r[1] for r in res) / wall)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_sample(n=8, C=512, sims=100, moves=1):
+    arm = CpuArm(n, C)
+    try:
+        arm.sample(sims, 1)  # warm: imports, thread pools, page-in
+        return arm.sample(sims, moves)
+    finally:
+        arm.close()
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synthetic_starts(engine_mod, n_games, seed, first_id, device):
+    """initial position + k in [0,8) random plies, k = slot % 8."""
+    b = np.zeros(n_games, dtype=np.uint64)
+    w = np.zeros(n_games, dtype=np.uint64)
+    p = np.zeros(n_games, dtype=np.int32)
+    for k in range(8):
+        sel = np.arange(n_games) % 8 == k
+        if not sel.any():
+            continue
+        out = engine_mod.perft_playouts(n_games, 8, seed=seed, first_game_id=first_id, max_moves=k, device=device)
+        b[sel] = out["black"][sel]; w[sel] = out["white"][sel]; p[sel] = out["player"][sel]
+    return b, w, p
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from othellozero_b200 import build as ozbuild
+    ozbuild.build()
+    from othellozero_b200 import engine as E, net as oznet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for --impl ours)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+    n, C, sims, G = 8, args.channels, args.sims, args.games
+    STEPS_PER_MOVE = sims
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "perft":
+        return run_perft(args, E, peaks, rank, world, local, barrier)
+
+    mode = E.PRIOR_NET if args.workload == "selfplay" else E.PRIOR_HASH
+    eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
+                   device=local)
+    if mode == E.PRIOR_NET:
+        # C1: rank 0 owns the weights, everyone else receives them over NCCL and folds them on device
+        nfl = oznet.blob_size(n, C)
+        if rank == 0:
+            wt = torch.from_numpy(oznet.init_weights(n, C, seed=0)).cuda(local)
+        else:
+            wt = torch.empty(nfl, dtype=torch.float32, device=f"cuda:{local}")
+        if world > 1:
+            dist.broadcast(wt, src=0)
+        torch.cuda.synchronize()
+        eng.load_weights_from_tensor(wt, C)
+        eng.set_timing(True)
+    first_id = rank * G
+    sb, sw, sp = synthetic_starts(E, G, args.seed, first_id, local)
+    ids = np.arange(first_id, first_id + G, dtype=np.uint64)
+    eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
+
+    stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{local}")
+    for _ in range(args.warmup):
+        eng.selfplay_run(STEPS_PER_MOVE)
+    eng.layer_times()  # reset the per-layer accumulators
+    barrier()
+    c0 = eng.counters(); l0 = eng.launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        active = eng.selfplay_run(STEPS_PER_MOVE)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    c1 = eng.counters(); l1 = eng.launches()
+    lt = eng.layer_times() if mode == E.PRIOR_NET else np.zeros(8, dtype=np.float32)
+    d_sims = c1["sims"] - c0["sims"]; d_nodes = c1["nodes"] - c0["nodes"]; d_moves = c1["moves"] - c0["moves"]
+    tree_steps = args.steps * STEPS_PER_MOVE
+
+    t = torch.tensor([ms, float(d_sims), float(d_nodes), float(d_moves), float(l1 - l0)], dtype=torch.float64,
+                     device=f"cuda:{local}")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0]); tot_sims, tot_nodes, tot_moves, tot_launch = (float(x) for x in tsum[1:])
+    else:
+        tot_sims, tot_nodes, tot_moves, tot_launch = float(d_sims), float(d_nodes), float(d_moves), float(l1 - l0)
+    sims_per_s = tot_sims / (ms / 1e3)
+
+    # ---- e2e: complete games through the public API with HOST buffers (copies inside) ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        eng.selfplay_begin(args.e2e_games, sims, 1.0, 0.9, args.e2e_moves, sb[:args.e2e_games], sw[:args.e2e_games],
+                           sp[:args.e2e_games], ids[:args.e2e_games])                      # H2D start positions
+        cb = eng.counters()
+        eng.selfplay_run(-1)
+        rec = eng.selfplay_records()                                                       # D2H example records
+        ce = eng.counters()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e_sims = ce["sims"] - cb["sims"]
+        h2d = int(sb[:args.e2e_games].nbytes + sw[:args.e2e_games].nbytes + sp[:args.e2e_games].nbytes + ids[:args.e2e_games].nbytes)
+        d2h = int(sum(rec[k].nbytes for k in ("black", "white", "action", "player", "n_moves", "winner")))
+        te = torch.tensor([dt, float(e_sims), float((rec["winner"] >= 0).sum()), float(rec["n_moves"].sum())],
+                          dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            m = te.clone(); dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            s = te.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            dt, e_sims, e_games, e_moves = float(m[0]), float(s[1]), float(s[2]), float(s[3])
+        else:
+            e_games, e_moves = float(te[2]), float(te[3])
+        e2e = {"value": e_sims / dt, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "games_per_s": e_games / dt, "games": int(e_games), "mean_plies": e_moves / max(1.0, args.e2e_games * world),
+               "seconds": dt, "what": f"{args.e2e_games} games/GPU from host start positions to host example records"
+                                      + ("" if args.e2e_moves < 0 else f", first {args.e2e_moves} moves")}
+    if world > 1:
+        # C2: gather per-rank example counts (the example payload itself is gathered by othellozero_b200.dist)
+        cnt = torch.tensor([int(tot_moves)], device=f"cuda:{local}")
+        dist.all_reduce(cnt)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+
+    out = {
+        "metric": "mcts_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if mode == E.PRIOR_NET else "f64", "data": "synthetic",
+        "config": {"workload": ("8x8 self-play, 100 sims/move, %d concurrent games per GPU, random-init OthelloNNet "
+                                "C=%d bf16 leaf eval (BASELINE.json configs[2])" % (G, C)) if mode == E.PRIOR_NET else
+                   "8x8 self-play tree+rules only, closed-form hash priors (no network)",
+                   "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
+                   "step": f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game",
+                   "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 336 / 1e9),
+                   "starts": "initial position + (game_id % 8) random plies", "parallelism": f"games sharded x{world}"},
+        "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
+        "net_evals_per_s": tot_nodes / (ms / 1e3), "evals_per_sim": tot_nodes / max(1.0, tot_sims),
+        "gpu_launches": int(tot_launch), "clocks": clocks,
+    }
+    if mode == E.PRIOR_NET:
+        avg_leaves = (d_nodes / max(1, tree_steps))
+        conv2_ms = float(lt[1])
+        achieved = FLOP_CONV2_PER_BOARD_8 * (C / 512.0) ** 2 * avg_leaves / (conv2_ms * 1e-3) / 1e12 if conv2_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        out["roofline"] = {"bound": "tensor", "kernel": "oz_gemm_kernel<256,relu> (conv2 implicit GEMM)",
+                           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                           "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": None,
+                           "avg_boards_per_launch": avg_leaves, "avg_launch_ms": conv2_ms,
+                           "layer_ms": {k: float(v) for k, v in zip(["conv1_gather", "conv2", "conv3", "conv4", "fc1", "fc2", "heads"], lt[:7])},
+                           "forwards_timed": int(lt[7]),
+                           "whole_step_tensor_frac": (tot_nodes / world) * FLOP_PER_EVAL_8 * (C / 512.0) ** 2 / (ms * 1e-3) / 1e12 / peak}
+    else:
+        out["roofline"] = {"bound": "hbm", "kernel": "tree_step_kernel", "achieved": sims_per_s / world * 1000 / 1e9,
+                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sims_per_s / world * 1000 / 1e9 / peaks["hbm_gbs"],
+                           "traffic": None, "note": "algorithmic ~1.0 KB/sim (SURVEY §8d); latency- not bandwidth-bound"}
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu and world >= 1:
+        out["cpu_baseline"] = cpu_sample(n, C, sims, moves=args.cpu_moves)
+    print(json.dumps(out))
+
+
+def run_perft(args, E, peaks, rank, world, local, barrier):
+    import torch
+    n_games = args.games if args.games > 4096 else (1 << 20)
+    b = torch.empty(n_games, dtype=torch.int64, device=f"cuda:{local}")
+    w = torch.empty_like(b)
+    info = torch.empty(n_games, dtype=torch.int32, device=f"cuda:{local}")
+    L = E._lib.load()
+    import ctypes as C
+
+    def launch(seed):
+        E.check(L.oz_perft_playouts_dev(8, seed, rank * n_games, n_games, -1, C.c_void_p(b.data_ptr()),
+                                        C.c_void_p(w.data_ptr()), C.c_void_p(info.data_ptr()), None, None))
+    for i in range(args.warmup):
+        launch(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    plies = 0
+    ev0.record()
+    for i in range(args.steps):
+        launch(100 + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    plies = int((info & 0xFF).sum().item()) * args.steps  # plies of the last launch x steps (same distribution)
+    if rank == 0:
+        print(json.dumps({"metric": "perft_plies_per_sec", "value": plies / (ms / 1e3) * world, "unit": "plies/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                          "data": "synthetic", "config": {"workload": "8x8 random-playout perft, %d concurrent games per GPU "
+                                                                    "(BASELINE.json configs[1])" % n_games},
+                          "gpu_launches": args.steps}))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm(8, args.channels)
+    try:
+        for _ in range(max(1, args.warmup)):
+            arm.sample(args.sims, 1)
+        t0 = time.perf_counter()
+        tot = 0.0
+        last = None
+        for _ in range(args.steps):
+            last = arm.sample(args.sims, args.cpu_moves)
+            tot += last["value"]
+        dt = time.perf_counter() - t0
+    finally:
+        arm.close()
+    v = tot / max(1, args.steps)
+    cb = dict(last); cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "mcts_sims_per_sec", "value": v, "unit": "sims/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "8x8 self-play, 100 sims/move, random-init OthelloNNet C=%d (BASELINE.json configs[2]); CPU "
+                               "arm = oracle port of the reference's sequential search + batch-1 fp32 net on all host "
+                               "cores; step = one move (100 sims) per process" % args.channels},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="selfplay", choices=["selfplay", "tree", "perft"])
+    ap.add_argument("--games", type=int, default=4096)
+    ap.add_argument("--sims", type=int, default=100)
+    ap.add_argument("--channels", type=int, default=512)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-games", type=int, default=4096)
+    ap.add_argument("--e2e-moves", type=int, default=-1)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-moves", type=int, default=1)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,7 @@ SIGNATURES = {
     "oz_net_get_activation": (C.c_int, [vp, C.c_int32, vp, C.c_int64]),
     "oz_engine_launches": (C.c_int, [vp, u64p]),
     "oz_net_layer_times": (C.c_int, [vp, f32p]),
+    "oz_net_set_timing": (C.c_int, [vp, C.c_int32]),
 }
 
 _lib = None

@@ -433,7 +433,13 @@ extern "C" int oz_net_forward_host(oz_engine* e, const uint64_t* own, const uint
 
 extern "C" int oz_net_layer_times(oz_engine* e, float* ms8) {
     OZ_REQUIRE(e && ms8, "null argument");
-    memcpy(ms8, e->layer_ms, sizeof(e->layer_ms));
+    OZ_CUDA(cudaSetDevice(e->cfg.device));
+    return oz_net_times(e, ms8);
+}
+
+extern "C" int oz_net_set_timing(oz_engine* e, int32_t on) {
+    OZ_REQUIRE(e, "null engine");
+    oz_net_set_timing_impl(e, on != 0);
     return OZ_OK;
 }
 

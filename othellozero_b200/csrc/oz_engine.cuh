@@ -119,6 +119,8 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
                    float* pi_dev, float* logits_dev, float* v_dev);
 int64_t oz_net_blob_floats_impl(int board_size, int channels);
 int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes);
+void oz_net_set_timing_impl(oz_engine* e, bool on);
+int oz_net_times(oz_engine* e, float* ms8);
 
 template <typename T>
 int oz_dev_alloc(oz_engine* e, T** p, size_t count) {

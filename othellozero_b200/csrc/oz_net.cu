@@ -450,10 +450,26 @@ struct OzNet {
     bf16 *w[6] = {nullptr}; float* bias[6] = {nullptr};  // conv2, conv3, conv4, fc1, fc2, heads
     bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *act4 = nullptr, *f1 = nullptr, *f2 = nullptr;
     OzLayer layer[6];
-    cudaEvent_t ev[8] = {nullptr};
+    // per-layer timing: a ring of event sets, harvested lazily so the stream is never blocked
+    static constexpr int RING = 8;
+    cudaEvent_t ev[RING][8] = {{nullptr}};
+    bool ev_used[RING] = {false};
+    int ev_next = 0;
+    double ms_sum[8] = {0};
+    long ms_cnt = 0;
     void* allocs[32];
     int n_allocs = 0;
 };
+
+static void oz_net_harvest(OzNet* net, int r) {
+    cudaEventSynchronize(net->ev[r][7]);  // RING forwards old when called from the hot loop: already complete
+    for (int i = 0; i < 7; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, net->ev[r][i], net->ev[r][i + 1]) == cudaSuccess) net->ms_sum[i] += ms;
+    }
+    net->ms_cnt++;
+    net->ev_used[r] = false;
+}
 
 static int net_alloc(OzNet* net, void** p, size_t bytes) {
     cudaError_t err = cudaMalloc(p, bytes + 256);
@@ -485,7 +501,8 @@ int oz_net_create(oz_engine* e) {
     net->timing = t && t[0] == '1';
     int dev = e->cfg.device;
     cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&net->ev[i]);
+    for (int r = 0; r < OzNet::RING; ++r)
+        for (int i = 0; i < 8; ++i) cudaEventCreate(&net->ev[r][i]);
     e->net = net;
     return OZ_OK;
 }
@@ -494,7 +511,8 @@ void oz_net_destroy(oz_engine* e) {
     OzNet* net = e->net;
     if (!net) return;
     for (int i = 0; i < net->n_allocs; ++i) cudaFree(net->allocs[i]);
-    for (int i = 0; i < 8; ++i) if (net->ev[i]) cudaEventDestroy(net->ev[i]);
+    for (int r = 0; r < OzNet::RING; ++r)
+        for (int i = 0; i < 8; ++i) if (net->ev[r][i]) cudaEventDestroy(net->ev[r][i]);
     delete net;
     e->net = nullptr;
 }
@@ -531,6 +549,7 @@ static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, in
     OzLayer& Lr = net->layer[li];
     GemmParams& p = Lr.p;
     memset(&p, 0, sizeof(p));
+    if (epi == EPI_RELU_BF16) block_n = (nout_pad % 256 == 0) ? 256 : 128;
     const int rows_per_board = ow * oh;
     int nb = BLOCK_M / rows_per_board;
     if (nb > 256) nb = 256;
@@ -560,7 +579,7 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
     OzNet* net = e->net;
     if (!net) { oz_set_error("engine was not created with OZ_PRIOR_NET"); return OZ_ERR_STATE; }
     const int n = net->n, C = channels, nsq = n * n, B = net->Bmax;
-    OZ_REQUIRE(C >= 64 && C % 64 == 0 && C <= 1024, "channels must be a multiple of 64 in [64,1024] (got %d)", C);
+    OZ_REQUIRE(C >= 128 && C % 128 == 0 && C <= 1024, "channels must be a multiple of 128 in [128,1024] (got %d)", C);
     const int64_t need = oz_net_blob_floats_impl(n, C);
     OZ_REQUIRE(n_floats == need, "weight blob has %lld floats, expected %lld", (long long)n_floats, (long long)need);
     if (net->loaded && net->C != C) { oz_set_error("channel count cannot change after the first load"); return OZ_ERR_STATE; }
@@ -590,6 +609,8 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<256, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmSmem<256>::DYN_BYTES));
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GemmSmem<128>::DYN_BYTES));
+        OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmSmem<128>::DYN_BYTES));
         OZ_CUDA(cudaMemsetAsync(net->w[5], 0, 128ull * 512 * 2, st));
         OZ_CUDA(cudaMemsetAsync(net->bias[5], 0, 128 * 4, st));
@@ -660,7 +681,13 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
     const int n = net->n, C = net->C, nsq = n * n;
     if (max_count > net->Bmax) max_count = net->Bmax;
     const bool tm = net->timing;
-    if (tm) cudaEventRecord(net->ev[0], st);
+    cudaEvent_t* ev = net->ev[net->ev_next];
+    if (tm) {
+        if (net->ev_used[net->ev_next]) oz_net_harvest(net, net->ev_next);
+        net->ev_used[net->ev_next] = true;
+        net->ev_next = (net->ev_next + 1) % OzNet::RING;
+        cudaEventRecord(ev[0], st);
+    }
     {
         long long warps = (long long)max_count * nsq;
         int blocks = (int)((warps + 7) / 8);
@@ -668,7 +695,7 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         OZ_CUDA(cudaGetLastError());
         e->launches++;
     }
-    if (tm) cudaEventRecord(net->ev[1], st);
+    if (tm) cudaEventRecord(ev[1], st);
     for (int li = 0; li < 6; ++li) {
         OzLayer& Lr = net->layer[li];
         GemmParams p = Lr.p;
@@ -678,18 +705,35 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         int tiles = ((max_count + p.nb - 1) / p.nb) * p.n_tiles;
         int grid = tiles < net->sm_count ? tiles : net->sm_count;
         if (grid < 1) grid = 1;
-        if (Lr.epi == EPI_RELU_BF16)
+        if (Lr.epi == EPI_RELU_BF16 && Lr.block_n == 256)
             oz_gemm_kernel<256, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<256>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+        else if (Lr.epi == EPI_RELU_BF16)
+            oz_gemm_kernel<128, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
         else
             oz_gemm_kernel<128, EPI_HEADS><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
-        if (tm) cudaEventRecord(net->ev[2 + li], st);
+        if (tm) cudaEventRecord(ev[2 + li], st);
     }
-    if (tm) {
-        cudaEventSynchronize(net->ev[7]);
-        for (int i = 0; i < 7; ++i) cudaEventElapsedTime(&e->layer_ms[i], net->ev[i], net->ev[i + 1]);
-    }
+    return OZ_OK;
+}
+
+void oz_net_set_timing_impl(oz_engine* e, bool on) {
+    if (e->net) e->net->timing = on;
+}
+
+// Average per-layer device time (ms) over the forwards recorded since the last call; [7] = forwards averaged.
+int oz_net_times(oz_engine* e, float* ms8) {
+    OzNet* net = e->net;
+    for (int i = 0; i < 8; ++i) ms8[i] = 0.f;
+    if (!net) return OZ_OK;
+    for (int r = 0; r < OzNet::RING; ++r)
+        if (net->ev_used[r]) oz_net_harvest(net, r);
+    if (net->ms_cnt > 0)
+        for (int i = 0; i < 7; ++i) ms8[i] = (float)(net->ms_sum[i] / (double)net->ms_cnt);
+    ms8[7] = (float)net->ms_cnt;
+    for (int i = 0; i < 8; ++i) net->ms_sum[i] = 0;
+    net->ms_cnt = 0;
     return OZ_OK;
 }
 

@@ -210,6 +210,17 @@ class Engine:
         check(self._L.oz_net_get_activation(self._h, layer, raw.ctypes.data_as(C.c_void_p), raw.nbytes))
         return (raw.astype(np.uint32) << 16).view(np.float32).reshape(n_boards, rows, channels)
 
+    def set_timing(self, on: bool):
+        check(self._L.oz_net_set_timing(self._h, int(on)))
+
+    def stream(self) -> int:
+        return int(self._L.oz_engine_stream(self._h) or 0)
+
+    def load_weights_from_tensor(self, t, channels: int):
+        """float32 CUDA tensor (e.g. just received by an NCCL broadcast) -> fold + cast on device."""
+        assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 4 and t.is_contiguous()
+        self.load_weights_dev(t.data_ptr(), t.numel(), channels)
+
     def layer_times(self):
         ms = np.zeros(8, dtype=np.float32)
         check(self._L.oz_net_layer_times(self._h, ptr(ms, f32p)))

@@ -1,0 +1,186 @@
+"""Episode side of the drop-in: ``training.execute_episode`` (training.py:26-72) and a ``workers.Worker``
+(workers.py:24-79) that plays all of its episodes as ONE batch on the GPU.
+
+    examples = execute_episode(board_size, neural_network, degree_exploration,
+                               num_simulations, policy_temperature, e_greedy)
+
+returns the reference's list of ``(board (N,N,2) bool, one-hot policy (N,N) float64, z)`` with the 8
+symmetries of training.py:13-23 in the reference's order.  Differences, all documented in INTEGRATION.md:
+boards are true per-move snapshots unless ``reference_aliasing=True`` (the reference aliases the live board,
+SURVEY §0.8); with e_greedy < 1 the random moves come from the engine's counter RNG, not CPython's.
+"""
+from __future__ import annotations
+
+import logging
+import threading
+import uuid
+
+import numpy as np
+
+from . import engine as _e
+from .mcts import HashPriorNet
+from .net import B200NNet, bits_to_board
+
+
+def training_example_symmetries(board, policy):
+    """training.py:13-23 (same order: rotations 1..4, flipped first)."""
+    out = []
+    for rotation in range(1, 5):
+        for flip in (True, False):
+            b = np.rot90(board, k=rotation)
+            p = np.rot90(policy, k=rotation)
+            if flip:
+                b = np.fliplr(b)
+                p = np.fliplr(p)
+            out.append((b, p))
+    return out
+
+
+getSymmetries = training_example_symmetries  # alpha-zero-general name
+
+
+def default_nodes_per_game(board_size: int, num_simulations: int) -> int:
+    # the reference never prunes: <= one new node per simulation for every move of the episode
+    return num_simulations * (board_size * board_size - 4) + 64
+
+
+class SelfPlay:
+    """A pool of concurrent self-play games on one GPU (one warp per game)."""
+
+    def __init__(self, board_size: int, neural_network, degree_exploration: float = 1.0, max_games: int = 4096,
+                 num_simulations: int = 100, device: int = 0, seed: int = 0, log_visits: bool = False):
+        self.board_size = board_size
+        self.num_simulations = num_simulations
+        if isinstance(neural_network, HashPriorNet):
+            mode = _e.PRIOR_HASH
+        elif isinstance(neural_network, B200NNet):
+            mode = _e.PRIOR_NET
+        else:
+            raise TypeError("device self-play needs a B200NNet or HashPriorNet; for any other net object use "
+                            "othellozero_b200.mcts.OthelloMCTS (host-evaluated priors)")
+        self.engine = _e.Engine(board_size, max_games=max_games,
+                                nodes_per_game=default_nodes_per_game(board_size, num_simulations), prior_mode=mode,
+                                c_puct=float(degree_exploration), seed=seed, device=device, log_visits=log_visits)
+        if mode == _e.PRIOR_NET:
+            self.engine.load_weights(neural_network.blob, neural_network.channels)
+
+    def set_weights(self, blob, channels):
+        self.engine.load_weights(blob, channels)
+
+    def play(self, n_games: int, policy_temperature: float = 1.0, e_greedy: float = 1.0, game_ids=None,
+             black=None, white=None, player=None, max_moves: int = -1) -> dict:
+        self.engine.selfplay_begin(n_games, self.num_simulations, policy_temperature, e_greedy, max_moves, black, white,
+                                   player, game_ids)
+        self.engine.selfplay_run(-1)
+        return self.engine.selfplay_records()
+
+    def close(self):
+        self.engine.close()
+
+
+def records_to_examples(rec: dict, game: int, board_size: int, reference_aliasing: bool = False):
+    """One game's records -> the reference's example list (training.py:58-72)."""
+    n = board_size
+    k = int(rec["n_moves"][game])
+    winner = int(rec["winner"][game])
+    examples = []
+    final_board = None
+    if reference_aliasing and k:
+        # every example of the reference is a view of the live board, i.e. shows the FINAL position
+        last = k - 1
+        fb = bits_to_board(rec["black"][game][last], rec["white"][game][last], n)
+        from .othello import OthelloGame, OthelloPlayer
+        a = int(rec["action"][game][last])
+        pl = OthelloPlayer.BLACK if int(rec["player"][game][last]) == 0 else OthelloPlayer.WHITE
+        OthelloGame.flip_board_squares(fb, pl, a >> 3, a & 7)
+        final_board = fb
+    for p in range(k):
+        board = final_board if reference_aliasing else bits_to_board(rec["black"][game][p], rec["white"][game][p], n)
+        a = int(rec["action"][game][p])
+        policy = np.zeros((n, n))
+        policy[a >> 3][a & 7] = 1
+        player = int(rec["player"][game][p])
+        z = 1 if winner == player else -1
+        for b, pol in training_example_symmetries(board, policy):
+            examples.append((b, pol, z))
+    return examples
+
+
+def execute_episodes(n_episodes, board_size, neural_network, degree_exploration, num_simulations, policy_temperature,
+                     e_greedy, device: int = 0, seed: int = 0, reference_aliasing: bool = False, game_ids=None):
+    """n_episodes x training.execute_episode as one GPU batch; returns a list of example lists."""
+    sp = SelfPlay(board_size, neural_network, degree_exploration, max_games=n_episodes,
+                  num_simulations=num_simulations, device=device, seed=seed)
+    try:
+        rec = sp.play(n_episodes, policy_temperature, e_greedy, game_ids=game_ids)
+    finally:
+        sp.close()
+    for g in range(n_episodes):
+        logging.info(f'Episode finished: game {g}, winner channel {int(rec["winner"][g])}.')
+    return [records_to_examples(rec, g, board_size, reference_aliasing) for g in range(n_episodes)]
+
+
+def execute_episode(board_size, neural_network, degree_exploration, num_simulations, policy_temperature, e_greedy,
+                    **kw):
+    """Drop-in for training.execute_episode (training.py:26-27)."""
+    return execute_episodes(1, board_size, neural_network, degree_exploration, num_simulations, policy_temperature,
+                            e_greedy, **kw)[0]
+
+
+# ---- workers.Worker plug-in (workers.py:18-79) --------------------------------------------------------------
+class WorkType:
+    EXECUTE_EPISODE = 'Execute Episode'
+    DUEL_BETWEEN_NEURAL_NETWORKS = 'Duel between Neural Networks'
+    EVALUATE_NEURAL_NETWORK = 'Evaluate Neural Network'
+
+
+class Worker:
+    """Mirror of workers.Worker's interface (workers.py:24-79) for use without the reference on sys.path."""
+
+    def __init__(self):
+        self._executor_thread = None
+        self._results = None
+        self._worker_manager = None
+
+    def run(self, work_type, iterations, *args, **kwargs):
+        self._results = []
+        self._executor_thread = threading.Thread(name=self.get_executor_thread_name(), target=self._run,
+                                                 args=(work_type, iterations, args, kwargs))
+        self._executor_thread.start()
+
+    def wait(self):
+        return self._executor_thread.join() if self._executor_thread else None
+
+    def get_results(self):
+        return self._results
+
+    def get_executor_thread_name(self):
+        return f'{self.__class__.__name__}-{str(uuid.uuid4()).split("-", 1)[0]}'
+
+
+def make_b200_worker(worker_base=Worker, device: int = 0, seed: int = 0):
+    """Builds a ``B200Worker`` class deriving from ``worker_base`` — pass the reference's ``workers.Worker`` so that
+    ``WorkerManager.add_worker``'s isinstance check (workers.py:186-190) accepts it."""
+
+    class B200Worker(worker_base):
+        def __init__(self):
+            super().__init__()
+            self.device = device
+            self.seed = seed
+
+        def _run(self, work_type, iterations, args, kwargs):
+            # workers.py:57-65 runs the target once per iteration; here all iterations are one GPU batch and
+            # _results still receives one entry per iteration (workers.py:54-55,180-184).
+            if work_type != WorkType.EXECUTE_EPISODE:
+                raise TypeError('B200Worker implements WorkType.EXECUTE_EPISODE; arena work types are "next" rows')
+            logging.info(f'Task {work_type}: {iterations} episodes as one GPU batch on cuda:{self.device}')
+            results = execute_episodes(iterations, *args, device=self.device, seed=self.seed, **kwargs)
+            self._results.extend(results)
+
+        def execute_episode(self, *args, **kwargs):
+            return execute_episode(*args, device=self.device, seed=self.seed, **kwargs)
+
+    return B200Worker
+
+
+B200Worker = make_b200_worker()

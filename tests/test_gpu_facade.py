@@ -1,0 +1,123 @@
+"""The reference-named Python surface (OthelloGame / OthelloMCTS / execute_episode / Worker) over the C-ABI,
+checked against golden vectors produced by the reference and against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+import prior_fns
+
+pytestmark = pytest.mark.gpu
+
+
+def test_othello_game_replays_golden_playouts(golden_playouts):
+    from othellozero_b200.othello import BoardView, OthelloGame, OthelloPlayer
+    for rec in golden_playouts[:6] + golden_playouts[-4:]:
+        n = rec["n"]
+        g = OthelloGame(n)
+        ref = oracle.lib()
+        for mv in rec["moves"]:
+            acts = [tuple(int(x) for x in a) for a in g.get_valid_actions()]
+            assert (mv // n, mv % n) in acts
+            assert acts == oracle.valid_actions(g.board(BoardView.TWO_CHANNELS),
+                                                0 if g.current_player is OthelloPlayer.BLACK else 1)
+            g.play(mv // n, mv % n)
+        assert g.has_finished()
+        assert oracle.board_to_bits(g.board(BoardView.TWO_CHANNELS)) == (int(rec["b"], 16), int(rec["w"], 16))
+        wp, pts = g.get_winning_player()
+        assert (0 if wp is OthelloPlayer.BLACK else 1, int(pts)) == (rec["winner"], rec["points"])
+        with pytest.raises(AssertionError):
+            g.play(0, 0)  # 'Game has ended' (Othello/__init__.py:143)
+
+
+def test_othello_static_api_and_aliases(golden_rules):
+    from othellozero_b200.othello import OthelloGame, OthelloPlayer
+    for rec in golden_rules["8"][5:40:7]:
+        board = oracle.bits_to_board(int(rec["b"], 16), int(rec["w"], 16), 8).astype(bool)
+        for ch, pl in ((0, OthelloPlayer.BLACK), (1, OthelloPlayer.WHITE)):
+            exp = rec[f"moves{ch}"]
+            acts = [tuple(int(x) for x in a) for a in OthelloGame.get_player_valid_actions(board, pl)]
+            assert [r * 8 + c for r, c in acts] == [m[0] for m in exp]
+            assert OthelloGame.getValidMoves(board, pl).sum() == len(exp)
+            for (r, c), m in zip(acts, exp):
+                nb = board.copy()
+                OthelloGame.flip_board_squares(nb, pl, r, c)
+                assert oracle.board_to_bits(nb) == (int(m[1], 16), int(m[2], 16))
+        assert OthelloGame.has_board_finished(board) == rec["finished"]
+        assert OthelloGame.getGameEnded(board) == (0 if not rec["finished"] else (1 if rec["winner"] == 0 else -1))
+    with pytest.raises(TypeError):
+        OthelloGame.get_player_valid_actions(board, 0)
+    assert np.array_equal(OthelloGame.getCanonicalForm(board, OthelloPlayer.WHITE)[..., 0], board[..., 1])
+    assert np.array_equal(OthelloGame.getInitBoard(6), oracle.initial_board(6).astype(bool))
+
+
+def test_mcts_facade_hash_prior(golden_roots):
+    from othellozero_b200.mcts import HashPriorNet, OthelloMCTS
+    from othellozero_b200.othello import OthelloGame, OthelloPlayer
+    rec = golden_roots[0]
+    n = rec["n"]
+    m = OthelloMCTS(n, HashPriorNet(), 1)
+    st = OthelloGame.initial_board(n)
+    for _ in range(rec["sims"]):
+        m.simulate(st, OthelloPlayer.BLACK)
+    assert m.N(st) == rec["ns"]
+    for a in m.get_state_actions(st):
+        assert m.N(st, a) == rec["visits"][a[0] * n + a[1]]
+    pol = m.get_policy_action_probabilities(st, 1)
+    exp = np.array(rec["visits"], dtype=float).reshape(n, n)
+    assert np.array_equal(pol, exp / exp.sum())
+    assert m.getActionProb(st, 0).sum() == 1
+    m.close()
+
+
+def test_mcts_facade_any_predict_object(golden_episodes):
+    """A plain object with .predict (like the reference's NNetWrapper) is called once per expanded node."""
+    from othellozero_b200.mcts import OthelloMCTS
+    from othellozero_b200.net import NeuralNets
+    from othellozero_b200.othello import OthelloGame, OthelloPlayer
+
+    class Net:
+        network_type = NeuralNets.ONN
+        calls = 0
+
+        def predict(self, board):
+            Net.calls += 1
+            return prior_fns.sha_prior(board)
+
+    rec = golden_episodes["sha_6_25"]
+    m = OthelloMCTS(6, Net(), 1)
+    st = OthelloGame.initial_board(6)
+    m.simulate(st, OthelloPlayer.BLACK, num_simulations=rec["sims"])
+    got = [m.N(st, (r, c)) if (r, c) in m.get_state_actions(st) else 0 for r in range(6) for c in range(6)]
+    assert got == rec["visits"][0]
+    assert Net.calls == rec["sims"]  # one node (= one predict) per simulation from a fresh tree
+    m.close()
+
+
+def test_execute_episode_dropin(golden_episodes):
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.selfplay import execute_episode
+    rec = golden_episodes["hash_6_25"]
+    n = rec["n"]
+    ex = execute_episode(n, HashPriorNet(), 1, rec["sims"], 1, 1.0)
+    assert len(ex) == 8 * len(rec["moves"])
+    moves = [int(np.argmax(ex[8 * i + 7][1])) for i in range(len(rec["moves"]))]  # identity symmetry is last
+    assert moves == rec["moves"]
+    for i, (board, pol, z) in enumerate(ex):
+        assert board.shape == (n, n, 2) and pol.shape == (n, n) and pol.sum() == 1 and z in (1, -1)
+    # z = +1 iff the mover is the winner
+    for i, p in enumerate(rec["players"]):
+        assert ex[8 * i][2] == (1 if p == rec["winner"] else -1)
+    # first example of the first move: rot90 + fliplr of the initial board
+    b0 = oracle.initial_board(n).astype(bool)
+    assert np.array_equal(ex[0][0], np.fliplr(np.rot90(b0, k=1)))
+
+
+def test_b200_worker_batches_episodes():
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.selfplay import B200Worker, WorkType
+    w = B200Worker()
+    w.run(WorkType.EXECUTE_EPISODE, 5, 6, HashPriorNet(), 1, 10, 1, 1.0)
+    w.wait()
+    res = w.get_results()
+    assert len(res) == 5 and all(len(r) % 8 == 0 and len(r) > 0 for r in res)
+    assert all(len(r) == len(res[0]) for r in res)  # e_greedy = 1.0 -> identical deterministic games
