@@ -197,7 +197,7 @@ def run_ours(args):
 
     mode = E.PRIOR_NET if args.workload == "selfplay" else E.PRIOR_HASH
     eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
-                   device=local)
+                   device=local, eval_cache_log2=args.eval_cache_log2 if mode == E.PRIOR_NET else 0)
     if mode == E.PRIOR_NET:
         # C1: rank 0 owns the weights, everyone else receives them over NCCL and folds them on device
         nfl = oznet.blob_size(n, C)
@@ -235,16 +235,19 @@ def run_ours(args):
     c1 = eng.counters(); l1 = eng.launches()
     lt = eng.layer_times() if mode == E.PRIOR_NET else np.zeros(8, dtype=np.float32)
     d_sims = c1["sims"] - c0["sims"]; d_nodes = c1["nodes"] - c0["nodes"]; d_moves = c1["moves"] - c0["moves"]
+    d_hits = c1["cache_hits"] - c0["cache_hits"]; d_alias = c1["cache_aliases"] - c0["cache_aliases"]
+    d_evals = d_nodes - d_hits - d_alias  # positions that actually went through the network
     tree_steps = args.steps * STEPS_PER_MOVE
 
-    t = torch.tensor([ms, float(d_sims), float(d_nodes), float(d_moves), float(l1 - l0)], dtype=torch.float64,
-                     device=f"cuda:{local}")
+    t = torch.tensor([ms, float(d_sims), float(d_evals), float(d_moves), float(l1 - l0), float(d_hits), float(d_alias)],
+                     dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0]); tot_sims, tot_nodes, tot_moves, tot_launch = (float(x) for x in tsum[1:])
+        ms = float(tmax[0]); tot_sims, tot_nodes, tot_moves, tot_launch, tot_hits, tot_alias = (float(x) for x in tsum[1:])
     else:
-        tot_sims, tot_nodes, tot_moves, tot_launch = float(d_sims), float(d_nodes), float(d_moves), float(l1 - l0)
+        tot_sims, tot_nodes, tot_moves, tot_launch, tot_hits, tot_alias = (float(d_sims), float(d_evals), float(d_moves),
+                                                                          float(l1 - l0), float(d_hits), float(d_alias))
     sims_per_s = tot_sims / (ms / 1e3)
 
     # ---- e2e: complete games through the public API with HOST buffers (copies inside) ----------------------------
@@ -291,15 +294,18 @@ def run_ours(args):
                                 "C=%d bf16 leaf eval (BASELINE.json configs[2])" % (G, C)) if mode == E.PRIOR_NET else
                    "8x8 self-play tree+rules only, closed-form hash priors (no network)",
                    "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
+                   "eval_cache_log2": args.eval_cache_log2,
                    "step": f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game",
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 336 / 1e9),
                    "starts": "initial position + (game_id % 8) random plies", "parallelism": f"games sharded x{world}"},
         "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
         "net_evals_per_s": tot_nodes / (ms / 1e3), "evals_per_sim": tot_nodes / max(1.0, tot_sims),
+        "eval_cache": {"log2_entries": args.eval_cache_log2, "hits": int(tot_hits), "same_step_shares": int(tot_alias),
+                       "note": "identical positions are evaluated once across games; outputs are unchanged"},
         "gpu_launches": int(tot_launch), "clocks": clocks,
     }
     if mode == E.PRIOR_NET:
-        avg_leaves = (d_nodes / max(1, tree_steps))
+        avg_leaves = (d_evals / max(1, tree_steps))
         conv2_ms = float(lt[1])
         achieved = FLOP_CONV2_PER_BOARD_8 * (C / 512.0) ** 2 * avg_leaves / (conv2_ms * 1e-3) / 1e12 if conv2_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
@@ -401,6 +407,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=1)
+    ap.add_argument("--eval-cache-log2", type=int, default=24)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

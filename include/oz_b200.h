@@ -63,6 +63,9 @@ typedef struct oz_engine_config {
                                 (training.py:32), i.e. <= sims * plies */
     int32_t prior_mode;      /* OZ_PRIOR_* */
     int32_t log_visits;      /* keep per-move root visit counts of self-play games (tests) */
+    int32_t eval_cache_log2; /* OZ_PRIOR_NET: log2(entries) of the cross-game evaluation cache (272 B/entry); 0 = off.
+                                Identical positions are evaluated once; results are unchanged. */
+    int32_t reserved;
     double c_puct;           /* degree_exploration (MCTS/__init__.py:27,168-170) */
     uint64_t seed;           /* engine RNG seed (epsilon-greedy, synthetic starts) */
 } oz_engine_config;
@@ -130,7 +133,7 @@ int oz_search_get_visits(oz_engine* e, int32_t* visits, int32_t* ns);
 int oz_search_get_root_stats(oz_engine* e, int32_t game, double* q, double* p, int32_t* qtag);
 int oz_search_get_status(oz_engine* e, int32_t* status);
 /* counters: [0] simulations completed, [1] nodes expanded (= net evaluations, othelo_mcts.py:82-88),
- * [2] terminal visits, [3] tree steps launched, [4] leaves evaluated by the net, [5] max depth seen,
+ * [2] terminal visits, [3] evaluation-cache hits, [4] leaves that shared another game's evaluation, [5] max depth seen,
  * [6] transposition hits, [7] moves played. */
 int oz_engine_counters(oz_engine* e, uint64_t* out8);
 

@@ -160,8 +160,10 @@ static int read_leaf_count(oz_engine* e, int* n) {
 
 // Evaluate the pending leaf batch with the device network (count stays on the device).
 static int eval_leaves_net(oz_engine* e) {
-    return oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games, e->leaf_pi, e->leaf_logits,
-                          e->leaf_v);
+    int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games, e->leaf_pi, e->leaf_logits,
+                            e->leaf_v);
+    if (rc) return rc;
+    return oz_tree_cache_publish(e);
 }
 
 static int search_pump(oz_engine* e, int32_t* n_leaves) {
@@ -386,12 +388,16 @@ extern "C" int64_t oz_net_blob_floats(int32_t board_size, int32_t channels) {
 extern "C" int oz_net_load_weights(oz_engine* e, const float* blob, int64_t n_floats, int32_t channels) {
     OZ_REQUIRE(e && blob, "null argument");
     OZ_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = oz_tree_cache_clear(e);  // cached priors belong to the old weights
+    if (rc) return rc;
     return oz_net_load(e, blob, n_floats, channels, false);
 }
 
 extern "C" int oz_net_load_weights_dev(oz_engine* e, const float* blob_dev, int64_t n_floats, int32_t channels) {
     OZ_REQUIRE(e && blob_dev, "null argument");
     OZ_CUDA(cudaSetDevice(e->cfg.device));
+    int rc = oz_tree_cache_clear(e);
+    if (rc) return rc;
     return oz_net_load(e, blob_dev, n_floats, channels, true);
 }
 

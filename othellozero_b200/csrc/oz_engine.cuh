@@ -71,6 +71,9 @@ struct OzTreeParams {
     u64* table; int table_log2;               // [G][1<<table_log2] : fingerprint<<32 | (node_off+1)
     // leaf batch
     u64* leaf_own; u64* leaf_opp; int* leaf_count; const float* leaf_pi; const float* leaf_v;
+    // cross-game evaluation cache (optional)
+    u64* cache_tags; u64* cache_keys; int* cache_leaf; float* cache_pi; float* cache_v; int* leaf_cache_idx;
+    int cache_log2_buckets;
     // self-play
     int num_sims; int max_moves; double e_greedy; u64 seed;
     u64* rec_black; u64* rec_white; unsigned char* rec_action; unsigned char* rec_player; int* rec_visits;
@@ -91,6 +94,7 @@ struct oz_engine {
     int table_log2 = 0;
     u64 arena_stride = 0;
     u64 launches = 0;
+    size_t cache_entries = 0;
     // device allocations (freed in destroy)
     void* allocs[64];
     int n_allocs = 0;
@@ -109,6 +113,8 @@ int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white,
 int oz_tree_step(oz_engine* e);  // one tree kernel launch
 int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev);
 int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev);
+int oz_tree_cache_publish(oz_engine* e);  // after a leaf batch has been evaluated
+int oz_tree_cache_clear(oz_engine* e);    // weights changed
 
 // net (oz_net.cu)
 int oz_net_create(oz_engine* e);

@@ -358,30 +358,42 @@ __global__ void conv1_table_kernel(const float* __restrict__ w1 /*[9][2][C]*/, c
 __global__ void __launch_bounds__(256)
 conv1_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count, int max_count,
                     int n, int C, const bf16* __restrict__ table, bf16* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // one CTA per board: 64 threads classify the 3x3 neighbourhoods, then all 256 stream table rows -> act1
+    __shared__ int s_pat[64];
     int L = *count;
     if (L > max_count) L = max_count;
     const int nsq = n * n;
-    if (w >= (long long)L * nsq) return;
-    const int b = (int)(w / nsq), pos = (int)(w - (long long)b * nsq);
-    const int y = pos / n, x = pos - y * n;
-    const u64 o = own[b], q = opp[b];
-    int pat = 0, mul = 1;
+    for (int b = blockIdx.x; b < L; b += gridDim.x) {
+        const u64 o = own[b], q = opp[b];
+        if (threadIdx.x < nsq) {
+            const int pos = threadIdx.x;
+            const int y = pos / n, x = pos - y * n;
+            int pat = 0, mul = 1;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-        const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-        int s = 0;
-        if (yy >= 0 && yy < n && xx >= 0 && xx < n) {
-            const int bit = yy * 8 + xx;
-            s = (int)((o >> bit) & 1ull) + 2 * (int)((q >> bit) & 1ull);
+            for (int t = 0; t < 9; ++t) {
+                const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                int s = 0;
+                if (yy >= 0 && yy < n && xx >= 0 && xx < n) {
+                    const int bit = yy * 8 + xx;
+                    s = (int)((o >> bit) & 1ull) + 2 * (int)((q >> bit) & 1ull);
+                }
+                pat += s * mul;
+                mul *= 3;
+            }
+            s_pat[pos] = pat;
         }
-        pat += s * mul;
-        mul *= 3;
+        __syncthreads();
+        const int cpr = C / 8;                 // 16-byte chunks per row
+        const int total = nsq * cpr;
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)b * nsq * C);
+        const uint4* tab = reinterpret_cast<const uint4*>(table);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int pos = i / cpr, within = i - pos * cpr;
+            dst[i] = __ldg(tab + (size_t)s_pat[pos] * cpr + within);
+        }
+        __syncthreads();
     }
-    const uint4* src = reinterpret_cast<const uint4*>(table + (size_t)pat * C);
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)w * C);
-    for (int i = lane; i < C / 8; i += 32) dst[i] = __ldg(src + i);
 }
 
 // ---- weight folding -------------------------------------------------------------------------------------
@@ -689,8 +701,8 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         cudaEventRecord(ev[0], st);
     }
     {
-        long long warps = (long long)max_count * nsq;
-        int blocks = (int)((warps + 7) / 8);
+        (void)nsq;
+        int blocks = max_count < net->sm_count * 8 ? max_count : net->sm_count * 8;  // 8 resident CTAs/SM, grid-stride
         conv1_gather_kernel<<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, net->table1, net->act1);
         OZ_CUDA(cudaGetLastError());
         e->launches++;

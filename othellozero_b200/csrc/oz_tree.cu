@@ -216,6 +216,85 @@ __device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, uns
     return true;
 }
 
+
+// ---- cross-game evaluation cache -----------------------------------------------------------------------
+// Identical positions give identical network outputs (the tower is row-independent), so one evaluation can
+// serve every game that reaches the position — in the same step (ALIAS: share the leaf-batch row) or later
+// (HIT: expand immediately from the cached priors, no network round trip).  Results are unchanged.
+// 8-way buckets of 64-bit tags: [63:2] fingerprint | [1:0] state (0 empty, 1 claiming, 2 pending, 3 ready).
+enum { CACHE_MISS = 0, CACHE_OWNER = 1, CACHE_ALIAS = 2, CACHE_HIT = 3 };
+
+__device__ __forceinline__ u64 cache_hash(u64 own, u64 opp) {
+    u64 h = (own ^ 0xD6E8FEB86659FD93ull) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 31;
+    h += opp * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 29;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 32;
+    return h;
+}
+
+__device__ int cache_probe(const OzTreeParams& P, u64 own, u64 opp, int lane, u64* fp_out, int* cidx, int* leaf) {
+    const u64 h = cache_hash(own, opp);
+    const u64 fp = (h | (1ull << 63)) >> 2;  // 62 bits, never zero
+    const u64 bucket = (h >> 3) & (((u64)1 << P.cache_log2_buckets) - 1ull);
+    volatile u64* tags = (volatile u64*)P.cache_tags + bucket * 8;
+    *fp_out = fp;
+    for (int attempt = 0; attempt < 4096; ++attempt) {
+        u64 t = (lane < 8) ? tags[lane] : 0ull;
+        unsigned match = __ballot_sync(FULLW, lane < 8 && (t >> 2) == fp);
+        unsigned empty = __ballot_sync(FULLW, lane < 8 && t == 0ull);
+        if (match) {
+            const int l = __ffs(match) - 1;
+            const int st = (int)(__shfl_sync(FULLW, t, l) & 3ull);
+            const int idx = (int)(bucket * 8) + l;
+            if (st == 1) {  // another game is publishing this very position right now: wait for it
+                __nanosleep(64);
+                continue;
+            }
+            __threadfence();
+            const volatile u64* key = (const volatile u64*)P.cache_keys + 2 * (size_t)idx;
+            if (key[0] != own || key[1] != opp) return CACHE_MISS;  // fingerprint collision: evaluate uncached
+            *cidx = idx;
+            if (st == 3) return CACHE_HIT;
+            *leaf = ((const volatile int*)P.cache_leaf)[idx];
+            return CACHE_ALIAS;
+        }
+        if (!empty) return CACHE_MISS;  // bucket full
+        const int l = __ffs(empty) - 1;
+        u64 old = 0;
+        if (lane == 0) old = atomicCAS((u64*)&tags[l], 0ull, (fp << 2) | 1ull);
+        old = __shfl_sync(FULLW, old, 0);
+        if (old == 0ull) {
+            *cidx = (int)(bucket * 8) + l;
+            return CACHE_OWNER;
+        }
+        // lost the race for this slot: look again (the winner may be the same position)
+    }
+    return CACHE_MISS;
+}
+
+// After the leaf batch has been evaluated: copy each owner's priors into its cache slot and mark it ready.
+__global__ void cache_publish_kernel(const OzTreeParams P) {
+    const int lane = threadIdx.x & 31;
+    const int li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int L = *P.leaf_count;
+    if (li >= L) return;
+    const int idx = P.leaf_cache_idx[li];
+    if (idx < 0) return;
+    float* dst = P.cache_pi + (size_t)idx * 64;
+    const float* src = P.leaf_pi + (size_t)li * 64;
+    dst[lane] = src[lane];
+    dst[lane + 32] = src[lane + 32];
+    if (lane == 0) P.cache_v[idx] = P.leaf_v[li];
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        u64 t = P.cache_tags[idx];
+        P.cache_tags[idx] = (t & ~3ull) | 3ull;
+    }
+}
+
 __device__ __forceinline__ void warp_argmax(double& u, int& j) {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
@@ -242,7 +321,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
     u64* table = P.table + ((size_t)slot << P.table_log2);
     const int n = P.n;
     int sims_left = P.sims_left[slot];
-    u64 c_sims = 0, c_nodes = 0, c_term = 0, c_trans = 0, c_moves = 0;
+    u64 c_sims = 0, c_nodes = 0, c_term = 0, c_trans = 0, c_moves = 0, c_hits = 0, c_alias = 0;
     int c_depth = 0;
     SimPath path{0, 0, 0, 0};
     Pending pd;
@@ -431,12 +510,44 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             --sims_left;
             continue;
         }
-        // hand the leaf to the evaluator and park this game
-        int li = 0;
-        if (lane == 0) li = atomicAdd(P.leaf_count, 1);
-        li = __shfl_sync(FULLW, li, 0);
+        // hand the leaf to the evaluator and park this game (or reuse an evaluation of the same position)
+        int li = -1, cidx = -1, cres = CACHE_MISS;
+        u64 cfp = 0;
+        if (P.cache_tags) {
+            cres = cache_probe(P, pd.own, pd.opp, lane, &cfp, &cidx, &li);
+            if (cres == CACHE_HIT) {
+                const int r = lane >> 3, c = lane & 7;
+                float pi_lo = 0.f, pi_hi = 0.f;
+                const float* row = P.cache_pi + (size_t)cidx * 64;
+                if (r < n && c < n) pi_lo = row[r * n + c];
+                if (r + 4 < n && c < n) pi_hi = row[(r + 4) * n + c];
+                const float v = P.cache_v[cidx];
+                if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
+                    status = OZ_GAME_POOL_FULL;
+                    break;
+                }
+                ++c_nodes; ++c_sims; ++c_hits;
+                --sims_left;
+                continue;
+            }
+        }
+        if (cres == CACHE_ALIAS) {
+            ++c_alias;
+        } else {
+            if (lane == 0) li = atomicAdd(P.leaf_count, 1);
+            li = __shfl_sync(FULLW, li, 0);
+            if (lane == 0) {
+                P.leaf_own[li] = pd.own; P.leaf_opp[li] = pd.opp;
+                if (P.cache_tags) P.leaf_cache_idx[li] = (cres == CACHE_OWNER) ? cidx : -1;
+                if (cres == CACHE_OWNER) {
+                    P.cache_keys[2 * (size_t)cidx] = pd.own; P.cache_keys[2 * (size_t)cidx + 1] = pd.opp;
+                    P.cache_leaf[cidx] = li;
+                    __threadfence();
+                    *((volatile u64*)P.cache_tags + cidx) = (cfp << 2) | 2ull;  // pending: same-step readers alias row li
+                }
+            }
+        }
         if (lane == 0) {
-            P.leaf_own[li] = pd.own; P.leaf_opp[li] = pd.opp;
             P.pend_own[slot] = pd.own; P.pend_opp[slot] = pd.opp; P.pend_legal[slot] = pd.legal;
             P.pend_parent[slot] = pd.parent; P.pend_edge[slot] = pd.pedge; P.pend_depth[slot] = pd.depth;
             P.pend_leaf[slot] = li;
@@ -457,6 +568,8 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         if (c_nodes) atomicAdd(&P.counters[1], c_nodes);
         if (c_term) atomicAdd(&P.counters[2], c_term);
         if (c_trans) atomicAdd(&P.counters[6], c_trans);
+        if (c_hits) atomicAdd(&P.counters[3], c_hits);
+        if (c_alias) atomicAdd(&P.counters[4], c_alias);
         if (c_moves) atomicAdd(&P.counters[7], c_moves);
         atomicMax(&P.counters[5], (u64)c_depth);
     }
@@ -550,6 +663,18 @@ int oz_tree_alloc(oz_engine* e) {
     A(rec_player, unsigned char, (size_t)G * 64)
     A(counters, u64, 8) A(n_active, int, 4)
     if (e->cfg.log_visits) { A(rec_visits, int, (size_t)G * 64 * 64) } else { P.rec_visits = nullptr; }
+    P.cache_tags = nullptr; P.cache_log2_buckets = 0;
+    if (e->cfg.eval_cache_log2 > 0 && e->cfg.prior_mode == OZ_PRIOR_NET) {
+        int lg = e->cfg.eval_cache_log2;
+        if (lg < 10) lg = 10;
+        if (lg > 28) lg = 28;
+        const size_t entries = (size_t)1 << lg;
+        A(cache_tags, u64, entries) A(cache_keys, u64, entries * 2) A(cache_leaf, int, entries)
+        A(cache_pi, float, entries * 64) A(cache_v, float, entries) A(leaf_cache_idx, int, G)
+        P.cache_log2_buckets = lg - 3;
+        e->cache_entries = entries;
+        OZ_CUDA(cudaMemsetAsync(P.cache_tags, 0, entries * sizeof(u64), e->stream));
+    }
 #undef A
     if ((rc = oz_dev_alloc<float>(e, &e->leaf_pi, (size_t)G * 64))) return rc;
     if ((rc = oz_dev_alloc<float>(e, &e->leaf_logits, (size_t)G * 64))) return rc;
@@ -670,5 +795,21 @@ int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int
     tree_root_stats_kernel<<<1, 32, 0, e->stream>>>(P, game, q_dev, p_dev, tag_dev, tag_dev + 64);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
+    return OZ_OK;
+}
+
+int oz_tree_cache_publish(oz_engine* e) {
+    OzTreeParams& P = e->tp;
+    if (!P.cache_tags) return OZ_OK;
+    cache_publish_kernel<<<(P.G + 7) / 8, 256, 0, e->stream>>>(P);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    return OZ_OK;
+}
+
+int oz_tree_cache_clear(oz_engine* e) {
+    OzTreeParams& P = e->tp;
+    if (!P.cache_tags) return OZ_OK;
+    OZ_CUDA(cudaMemsetAsync(P.cache_tags, 0, e->cache_entries * sizeof(u64), e->stream));
     return OZ_OK;
 }

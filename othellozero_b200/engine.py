@@ -63,7 +63,7 @@ class Engine:
 
     def __init__(self, board_size: int = 8, max_games: int = 1, nodes_per_game: int = 8192,
                  prior_mode: int = PRIOR_HASH, c_puct: float = 1.0, seed: int = 0, device: int = 0,
-                 log_visits: bool = False):
+                 log_visits: bool = False, eval_cache_log2: int = 0):
         self._L = _lib.load()
         self.board_size = board_size
         self.nsq = board_size * board_size
@@ -72,7 +72,7 @@ class Engine:
         self.device = device
         self.log_visits = log_visits
         cfg = _lib.EngineConfig(device, board_size, max_games, nodes_per_game, prior_mode, int(log_visits),
-                                float(c_puct), seed & M64)
+                                int(eval_cache_log2), 0, float(c_puct), seed & M64)
         h = C.c_void_p()
         check(self._L.oz_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -140,7 +140,7 @@ class Engine:
     def counters(self) -> dict:
         c = np.zeros(8, dtype=np.uint64)
         check(self._L.oz_engine_counters(self._h, ptr(c, u64p)))
-        names = ["sims", "nodes", "terminal_visits", "tree_steps", "net_leaves", "max_depth", "transpositions", "moves"]
+        names = ["sims", "nodes", "terminal_visits", "cache_hits", "cache_aliases", "max_depth", "transpositions", "moves"]
         return {k: int(x) for k, x in zip(names, c)}
 
     def launches(self) -> int:

@@ -122,3 +122,27 @@ def test_selfplay_with_net_matches_oracle_search():
     assert int(out["winner"][0]) == ref["winner"]
     assert e.counters()["nodes"] == 4 * ref["net_calls"]
     e.close(); pe.close()
+
+
+def test_eval_cache_is_results_preserving():
+    """Cross-game evaluation cache: identical positions are evaluated once; records must not change."""
+    from othellozero_b200 import engine, net
+    n, C, sims, G = 6, 128, 16, 96
+    blob = net.init_weights(n, C, seed=11, randomize_bn=True)
+    ids = np.arange(G, dtype=np.uint64) + 7000
+    outs, ctr = [], []
+    for lg in (0, 16):
+        e = engine.Engine(n, max_games=G, nodes_per_game=sims * 40, prior_mode=engine.PRIOR_NET, seed=5,
+                          log_visits=True, eval_cache_log2=lg)
+        e.load_weights(blob, C)
+        e.selfplay_begin(G, sims, 1.0, 0.8, -1, None, None, None, ids)   # all games start at the initial position
+        assert e.selfplay_run(-1) == 0
+        outs.append(e.selfplay_records())
+        ctr.append(e.counters())
+        e.close()
+    a, b = outs
+    for k in ("black", "white", "action", "player", "n_moves", "winner", "visits"):
+        assert np.array_equal(a[k], b[k]), k
+    assert ctr[0]["cache_hits"] == 0 and ctr[0]["cache_aliases"] == 0
+    assert ctr[1]["cache_hits"] + ctr[1]["cache_aliases"] > 0
+    assert ctr[0]["nodes"] == ctr[1]["nodes"] and ctr[0]["sims"] == ctr[1]["sims"]
