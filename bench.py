@@ -37,6 +37,26 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first matching launch in the committed ncu --set full
+    capture (profiles/r1_ncu_gemm_raw.csv; captured at 4096 boards per launch)."""
+    import csv
+    p = os.path.join(ROOT, "profiles", "r1_ncu_gemm_raw.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[ik]:
+                return {"bytes_per_launch": float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]],
+                        "at_boards_per_launch": 4096, "algorithmic_bytes": 2 * 4096 * 64 * 512 * 2,
+                        "source": "profiles/r1_ncu_gemm_raw.csv"}
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (C restatement of the reference's search + PyTorch fp32 batch-1 net), one process
 # per host core, each playing the first moves of an 8x8 / 100-sim episode.
@@ -216,23 +236,41 @@ def run_ours(args):
     eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
 
     stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{local}")
+    tree_only = mode == E.PRIOR_HASH
+    zero = {k: 0 for k in ("sims", "nodes", "moves", "cache_hits", "cache_aliases")}
+
+    def tree_batch():
+        # hash priors: a whole game runs inside ONE tree kernel launch, so a step is one complete batch of games
+        eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
+        eng.selfplay_run(-1)
+        return eng.counters()
+
     for _ in range(args.warmup):
-        eng.selfplay_run(STEPS_PER_MOVE)
+        tree_batch() if tree_only else eng.selfplay_run(STEPS_PER_MOVE)
     eng.layer_times()  # reset the per-layer accumulators
     barrier()
-    c0 = eng.counters(); l0 = eng.launches()
+    c0 = dict(zero) if tree_only else eng.counters()
+    l0 = eng.launches()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
+    c1 = dict(zero)
     for _ in range(args.steps):
-        active = eng.selfplay_run(STEPS_PER_MOVE)
+        if tree_only:
+            cc = tree_batch()
+            for k in c1:
+                c1[k] += cc[k]
+        else:
+            eng.selfplay_run(STEPS_PER_MOVE)
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
-    c1 = eng.counters(); l1 = eng.launches()
+    if not tree_only:
+        c1 = eng.counters()
+    l1 = eng.launches()
     lt = eng.layer_times() if mode == E.PRIOR_NET else np.zeros(8, dtype=np.float32)
     d_sims = c1["sims"] - c0["sims"]; d_nodes = c1["nodes"] - c0["nodes"]; d_moves = c1["moves"] - c0["moves"]
     d_hits = c1["cache_hits"] - c0["cache_hits"]; d_alias = c1["cache_aliases"] - c0["cache_aliases"]
@@ -278,10 +316,13 @@ def run_ours(args):
                "games_per_s": e_games / dt, "games": int(e_games), "mean_plies": e_moves / max(1.0, args.e2e_games * world),
                "seconds": dt, "what": f"{args.e2e_games} games/GPU from host start positions to host example records"
                                       + ("" if args.e2e_moves < 0 else f", first {args.e2e_moves} moves")}
+    gathered = None
     if world > 1:
-        # C2: gather per-rank example counts (the example payload itself is gathered by othellozero_b200.dist)
-        cnt = torch.tensor([int(tot_moves)], device=f"cuda:{local}")
-        dist.all_reduce(cnt)
+        # C2: all-gather of the packed example records over NCCL (outside the timed regions)
+        from othellozero_b200 import dist as ozd
+        if e2e is not None:
+            gathered = int(ozd.gather_examples(ozd.pack_records(rec)).shape[0])
+        dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
@@ -295,7 +336,8 @@ def run_ours(args):
                    "8x8 self-play tree+rules only, closed-form hash priors (no network)",
                    "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
                    "eval_cache_log2": args.eval_cache_log2,
-                   "step": f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game",
+                   "step": (f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
+                            if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 336 / 1e9),
                    "starts": "initial position + (game_id % 8) random plies", "parallelism": f"games sharded x{world}"},
         "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
@@ -304,6 +346,9 @@ def run_ours(args):
                        "note": "identical positions are evaluated once across games; outputs are unchanged"},
         "gpu_launches": int(tot_launch), "clocks": clocks,
     }
+    if gathered is not None:
+        out["nccl"] = {"weights_broadcast_floats": int(oznet.blob_size(n, C)) if mode == E.PRIOR_NET else 0,
+                       "examples_gathered": gathered}
     if mode == E.PRIOR_NET:
         avg_leaves = (d_evals / max(1, tree_steps))
         conv2_ms = float(lt[1])
@@ -311,7 +356,7 @@ def run_ours(args):
         peak = peaks["bf16_sustained"]
         out["roofline"] = {"bound": "tensor", "kernel": "oz_gemm_kernel<256,relu> (conv2 implicit GEMM)",
                            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                           "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": None,
+                           "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": ncu_traffic("oz_gemm_kernel<256, 0>"),
                            "avg_boards_per_launch": avg_leaves, "avg_launch_ms": conv2_ms,
                            "layer_ms": {k: float(v) for k, v in zip(["conv1_gather", "conv2", "conv3", "conv4", "fc1", "fc2", "heads"], lt[:7])},
                            "forwards_timed": int(lt[7]),

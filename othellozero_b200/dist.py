@@ -31,16 +31,16 @@ def broadcast_weights(blob, src: int = 0, device=None):
 
 
 def pack_records(rec: dict) -> np.ndarray:
-    """Self-play records -> compact int64 rows [black, white, action | player<<8 | z_black<<16 | game<<32] per move
+    """Self-play records -> compact uint64 rows [black, white, action | player<<8 | winner<<16 | game<<32] per move
     (18 B of information per position)."""
-    rows = []
-    for g in range(rec["n_moves"].shape[0]):
-        k = int(rec["n_moves"][g])
-        win = int(rec["winner"][g])
-        for p in range(k):
-            meta = int(rec["action"][g][p]) | (int(rec["player"][g][p]) << 8) | ((win & 0xFF) << 16) | (g << 32)
-            rows.append((int(rec["black"][g][p]), int(rec["white"][g][p]), meta))
-    return np.array(rows, dtype=np.uint64).reshape(-1, 3)
+    nm = np.asarray(rec["n_moves"]).astype(np.int64)
+    g = nm.shape[0]
+    valid = np.arange(64)[None, :] < nm[:, None]
+    gi = np.broadcast_to(np.arange(g, dtype=np.uint64)[:, None], (g, 64))
+    win = np.broadcast_to((np.asarray(rec["winner"]).astype(np.int64) & 0xFF).astype(np.uint64)[:, None], (g, 64))
+    meta = rec["action"].astype(np.uint64) | (rec["player"].astype(np.uint64) << np.uint64(8)) | \
+        (win << np.uint64(16)) | (gi << np.uint64(32))
+    return np.stack([rec["black"][valid].astype(np.uint64), rec["white"][valid].astype(np.uint64), meta[valid]], axis=1)
 
 
 def gather_examples(packed: np.ndarray, device=None) -> np.ndarray:
@@ -50,7 +50,7 @@ def gather_examples(packed: np.ndarray, device=None) -> np.ndarray:
     backend = dist.get_backend()
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else "cpu")
     world = dist.get_world_size()
-    mine = torch.as_tensor(packed.astype(np.int64).reshape(-1, 3)).to(dev)
+    mine = torch.as_tensor(np.ascontiguousarray(packed).view(np.int64).reshape(-1, 3)).to(dev)
     cnt = torch.tensor([mine.shape[0]], dtype=torch.int64, device=dev)
     cnts = [torch.zeros_like(cnt) for _ in range(world)]
     dist.all_gather(cnts, cnt)
@@ -60,4 +60,4 @@ def gather_examples(packed: np.ndarray, device=None) -> np.ndarray:
     bufs = [torch.zeros_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad)
     out = [b[:int(c.item())].cpu().numpy() for b, c in zip(bufs, cnts)]
-    return np.concatenate(out, axis=0).astype(np.uint64) if out else np.zeros((0, 3), dtype=np.uint64)
+    return np.concatenate(out, axis=0).view(np.uint64) if out else np.zeros((0, 3), dtype=np.uint64)
