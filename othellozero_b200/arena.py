@@ -1,0 +1,144 @@
+"""Arena ("next" row): agents and duels of agents.py:11-84 on top of the CUDA engine.
+
+* ``OthelloAgent`` / ``RandomOthelloAgent`` / ``NeuralNetworkOthelloAgent`` / ``duel_between_agents`` mirror the
+  reference game by game (same names, same semantics: the network agent always plays at temperature 0 with
+  ``random.choice`` over the arg-max set, agents.py:44-68, othelo_mcts.py:54-62).
+* ``pit`` plays many network-vs-network games at once: two engines (each agent keeps its own tree for the whole
+  game, agents.py:49), one search launch per move for all games whose turn it is.
+
+The reference's own drivers ``training.duel_between_neural_networks`` / ``evaluate_neural_network`` are broken
+(SURVEY §0.8); ``pit`` follows the working semantics of main.py:165-197 (who won, counted per game).
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+from . import engine as _e
+from .mcts import HashPriorNet, OthelloMCTS
+from .net import B200NNet
+from .othello import BoardView, OthelloGame, OthelloPlayer
+
+
+class OthelloAgent:
+    def __init__(self, game):
+        self.game = game
+
+    def play(self):
+        raise NotImplementedError
+
+
+class RandomOthelloAgent(OthelloAgent):
+    """agents.py:20-24."""
+
+    def play(self):
+        possible_moves = tuple(self.game.get_valid_actions())
+        move = random.choice(possible_moves)
+        self.game.play(*move)
+
+
+class NeuralNetworkOthelloAgent(OthelloAgent):
+    """agents.py:44-68 (temperature is forced to 0 there, :46)."""
+
+    def __init__(self, game, neural_network, num_simulations, degree_exploration, temperature=0):
+        self.temperature = 0
+        self.neural_network = neural_network
+        self.num_simulations = num_simulations
+        self.mcts = OthelloMCTS(game.board_size, neural_network, degree_exploration)
+        super().__init__(game)
+
+    def play(self):
+        state = self.game.board(BoardView.TWO_CHANNELS)
+        self.mcts.simulate(state, self.game.current_player, num_simulations=self.num_simulations)
+        if self.game.current_player == OthelloPlayer.WHITE:
+            state = OthelloGame.invert_board(state)
+        action_probabilities = self.mcts.get_policy_action_probabilities(state, self.temperature)
+        valid_actions = self.game.get_valid_actions()
+        best_action = max(valid_actions, key=lambda position: action_probabilities[tuple(position)])
+        self.game.play(*best_action)
+
+
+def duel_between_agents(game, agent_1, agent_2):
+    """agents.py:71-84: agent_1 is BLACK, agent_2 WHITE; returns (winning agent, points)."""
+    players_agents = {OthelloPlayer.BLACK: agent_1, OthelloPlayer.WHITE: agent_2}
+    while not game.has_finished():
+        players_agents[game.current_player].play()
+    winner, points = game.get_winning_player()
+    return players_agents[winner], points
+
+
+def _mode_for(net):
+    if isinstance(net, HashPriorNet):
+        return _e.PRIOR_HASH
+    if isinstance(net, B200NNet):
+        return _e.PRIOR_NET
+    raise TypeError("pit() needs B200NNet or HashPriorNet agents")
+
+
+def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1, n_games=64, device=0, rng=None,
+        start_black=None, start_white=None, start_player=None):
+    """n_games simultaneous duels, net_black playing BLACK.  Returns dict(winner [n_games] 0/1, black, white, plies).
+    Ties in the visit counts are broken with ``rng.choice`` (default: Python's ``random``) like the reference."""
+    rng = rng or random
+    n = board_size
+    nodes = num_simulations * (n * n) + 64
+    engines = []
+    for net in (net_black, net_white):
+        mode = _mode_for(net)
+        e = _e.Engine(n, max_games=n_games, nodes_per_game=nodes, prior_mode=mode, c_puct=float(degree_exploration),
+                      device=device)
+        if mode == _e.PRIOR_NET:
+            e.load_weights(net.blob, net.channels)
+        engines.append(e)
+    if start_black is None:
+        b0, w0 = OthelloGame.initial_board(n), None
+        from .othello import _bits
+        bb, ww = _bits(b0)
+        black = np.full(n_games, bb, dtype=np.uint64)
+        white = np.full(n_games, ww, dtype=np.uint64)
+        player = np.zeros(n_games, dtype=np.int32)
+    else:
+        black = np.array(start_black, dtype=np.uint64)
+        white = np.array(start_white, dtype=np.uint64)
+        player = np.array(start_player, dtype=np.int32)
+    for e in engines:
+        e.reset(n_games, black, white, player)
+    finished = np.zeros(n_games, dtype=bool)
+    plies = np.zeros(n_games, dtype=np.int32)
+    try:
+        while not finished.all():
+            for side, e in enumerate(engines):
+                turn = (~finished) & (player == side)
+                if not turn.any():
+                    continue
+                # games where it is not this agent's turn get a root with no legal move for the mover: the kernel
+                # skips them (0 simulations), exactly like an agent that is not asked to play
+                rb = np.where(turn, black, 0).astype(np.uint64)
+                rw = np.where(turn, white, 0).astype(np.uint64)
+                e.set_roots(rb, rw, player)
+                e.search(num_simulations)
+                visits, _ = e.visits()
+                idx = np.nonzero(turn)[0]
+                sq = np.zeros(idx.size, dtype=np.int32)
+                for j, g in enumerate(idx):
+                    v = visits[g]
+                    bests = np.nonzero(v == v.max())[0]
+                    sq[j] = int(bests[0]) if bests.size == 1 else int(rng.choice(list(bests)))
+                own = np.where(player[idx] == 0, black[idx], white[idx])
+                opp = np.where(player[idx] == 0, white[idx], black[idx])
+                o2, p2, fl, _ = _e.apply_moves(own, opp, sq, n, device)
+                assert not (fl & 0x80000000).any()
+                swapped = (fl & 1).astype(bool)
+                npl = np.where(swapped, 1 - player[idx], player[idx]).astype(np.int32)
+                black[idx] = np.where(npl == 0, o2, p2)
+                white[idx] = np.where(npl == 0, p2, o2)
+                player[idx] = npl
+                plies[idx] += 1
+                finished[idx] = (fl & 4) != 0
+    finally:
+        for e in engines:
+            e.close()
+    cb = np.array([bin(int(x)).count("1") for x in black])
+    cw = np.array([bin(int(x)).count("1") for x in white])
+    return dict(winner=np.where(cb >= cw, 0, 1), black=black, white=white, plies=plies, points=np.maximum(cb, cw))

@@ -121,3 +121,60 @@ def test_b200_worker_batches_episodes():
     res = w.get_results()
     assert len(res) == 5 and all(len(r) % 8 == 0 and len(r) > 0 for r in res)
     assert all(len(r) == len(res[0]) for r in res)  # e_greedy = 1.0 -> identical deterministic games
+
+
+class _FirstChoice:
+    @staticmethod
+    def choice(seq):
+        return seq[0]
+
+
+def _oracle_duel(n, sims, c_black=1.0, c_white=1.0):
+    """duel_between_agents (agents.py:71-84) with two NeuralNetworkOthelloAgents, restated with the oracle."""
+    trees = [oracle.Mcts(n, c_black), oracle.Mcts(n, c_white)]
+    board, player, moves = oracle.initial_board(n), 0, []
+    while not oracle.has_finished(board):
+        m = trees[player]
+        for _ in range(sims):
+            m.simulate(board, player)
+        canon = board if player == 0 else board[..., ::-1]
+        _, v = m.visits(np.ascontiguousarray(canon))
+        a = int(np.argmax(v.ravel()))            # T = 0, first of the arg-max set
+        moves.append(a)
+        board = oracle.flip_board(board, player, a // n, a % n)
+        nxt = 1 - player
+        if not oracle.valid_actions(board, nxt):
+            nxt = player
+        player = nxt
+    return moves, oracle.winner(board), oracle.board_to_bits(board)
+
+
+def test_arena_pit_matches_oracle_duel():
+    from othellozero_b200.arena import pit
+    from othellozero_b200.mcts import HashPriorNet
+    n, sims = 6, 20
+    moves, (wch, pts), (fb, fw) = _oracle_duel(n, sims)
+    out = pit(n, HashPriorNet(), HashPriorNet(), sims, 1, n_games=3, rng=_FirstChoice)
+    assert out["winner"].tolist() == [wch] * 3
+    assert [int(x) for x in out["black"]] == [fb] * 3 and [int(x) for x in out["white"]] == [fw] * 3
+    assert out["plies"].tolist() == [len(moves)] * 3 and out["points"].tolist() == [pts] * 3
+
+
+def test_agents_mirror_duel(monkeypatch):
+    import random
+    from othellozero_b200.arena import NeuralNetworkOthelloAgent, RandomOthelloAgent, duel_between_agents
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.othello import OthelloGame
+    n, sims = 6, 20
+    moves, (wch, pts), (fb, fw) = _oracle_duel(n, sims)
+    monkeypatch.setattr(random, "choice", lambda seq: seq[0])
+    game = OthelloGame(n)
+    a1 = NeuralNetworkOthelloAgent(game, HashPriorNet(), sims, 1)
+    a2 = NeuralNetworkOthelloAgent(game, HashPriorNet(), sims, 1)
+    winner, points = duel_between_agents(game, a1, a2)
+    assert (winner is a1) == (wch == 0) and int(points) == pts
+    from othellozero_b200.othello import BoardView
+    assert oracle.board_to_bits(game.board(BoardView.TWO_CHANNELS)) == (fb, fw)
+    g2 = OthelloGame(n)
+    w2, _ = duel_between_agents(g2, RandomOthelloAgent(g2), RandomOthelloAgent(g2))
+    assert g2.has_finished()

@@ -146,3 +146,30 @@ def test_eval_cache_is_results_preserving():
     assert ctr[0]["cache_hits"] == 0 and ctr[0]["cache_aliases"] == 0
     assert ctr[1]["cache_hits"] + ctr[1]["cache_aliases"] > 0
     assert ctr[0]["nodes"] == ctr[1]["nodes"] and ctr[0]["sims"] == ctr[1]["sims"]
+
+
+def test_config0_6x6_25sims_c512_episode():
+    """BASELINE configs[0]: 6x6, 25 sims/move, random-init OthelloNNet (C=512), one self-play game; the oracle search
+    fed the same device priors must replay it move for move."""
+    from othellozero_b200 import engine, net
+    n, C, sims = 6, 512, 25
+    blob = net.init_weights(n, C, seed=0)
+    e = engine.Engine(n, max_games=1, nodes_per_game=sims * 40, prior_mode=engine.PRIOR_NET, log_visits=True)
+    e.load_weights(blob, C)
+    e.selfplay_begin(1, sims, 1.0, 1.0)
+    assert e.selfplay_run(-1) == 0
+    out = e.selfplay_records()
+
+    def predict(board):
+        own, opp = net.boards_to_bits(board)
+        pi, _, v = e.net_forward(own, opp, want_logits=False)
+        return pi[0].reshape(n, n), v[0]
+
+    ref = oracle.execute_episode(n, sims, predict=predict, log_visits=True)
+    k = int(out["n_moves"][0])
+    assert [int(a) for a in out["action"][0][:k]] == [(a // n) * 8 + a % n for a in ref["moves"]]
+    for p in range(k):
+        got = [int(out["visits"][0][p][r * 8 + c]) for r in range(n) for c in range(n)]
+        assert got == ref["visits"][p].tolist()
+    assert int(out["winner"][0]) == ref["winner"]
+    e.close()

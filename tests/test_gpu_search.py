@@ -150,3 +150,53 @@ def test_pool_exhaustion_is_reported(E):
     with pytest.raises(MemoryError):
         e.selfplay_run(-1)
     e.close()
+
+
+def test_selfplay_full_size_properties(E):
+    """BASELINE configs[2] size (4096 games x 100 sims/move, 8x8) with the closed-form priors: size-independent
+    invariants for every game + oracle comparison for a sample."""
+    from othellozero_b200 import engine as eng_mod
+    G, sims, n = 4096, 100, 8
+    starts = [eng_mod.perft_playouts(G, n, seed=3, first_game_id=0, max_moves=k) for k in range(8)]
+    sel = np.arange(G) % 8
+    black = np.choose(sel, [s["black"] for s in starts]).astype(np.uint64)
+    white = np.choose(sel, [s["white"] for s in starts]).astype(np.uint64)
+    player = np.choose(sel, [s["player"] for s in starts]).astype(np.int32)
+    ids = np.arange(G, dtype=np.uint64)
+    e = E.Engine(n, G, sims * 61 + 64, E.PRIOR_HASH, seed=17)
+    e.selfplay_begin(G, sims, 1.0, 0.9, -1, black, white, player, ids)
+    assert e.selfplay_run(-1) == 0
+    rec = e.selfplay_records()
+    c = e.counters()
+    fb, fw, fp = e.positions()
+    e.close()
+    nm = rec["n_moves"]
+    assert (rec["winner"] >= 0).all() and (nm > 0).all() and (nm <= 60).all()
+    assert c["moves"] == int(nm.sum())
+    assert c["sims"] == sims * int(nm.sum())            # exactly `sims` simulations before every move
+    # replay every recorded move through the K2 rules kernel: positions must chain and end at the final position
+    for p in range(int(nm.max())):
+        act = nm > p
+        idx = np.nonzero(act)[0]
+        b, w, pl = rec["black"][idx, p], rec["white"][idx, p], rec["player"][idx, p].astype(np.int64)
+        own = np.where(pl == 0, b, w); opp = np.where(pl == 0, w, b)
+        o2, p2, fl, _ = eng_mod.apply_moves(own, opp, rec["action"][idx, p].astype(np.int32), n)
+        assert not (fl & 0x80000000).any()               # every recorded action was legal
+        swapped = (fl & 1).astype(bool)
+        npl = np.where(swapped, 1 - pl, pl)
+        nb = np.where(npl == 0, o2, p2); nw = np.where(npl == 0, p2, o2)
+        last = nm[idx] == p + 1
+        assert ((fl & 4) != 0).tolist() == last.tolist() # finished exactly at the last recorded move
+        nxt = idx[~last]
+        assert np.array_equal(nb[~last], rec["black"][nxt, p + 1]) and np.array_equal(nw[~last], rec["white"][nxt, p + 1])
+        assert np.array_equal(npl[~last], rec["player"][nxt, p + 1].astype(np.int64))
+        assert np.array_equal(nb[last], fb[idx[last]]) and np.array_equal(nw[last], fw[idx[last]])
+    pc = np.array([bin(int(x)).count("1") for x in fb]) >= np.array([bin(int(x)).count("1") for x in fw])
+    assert np.array_equal(rec["winner"], np.where(pc, 0, 1))  # draw -> BLACK
+    for g in (0, 1, 2047, 4095):
+        ref = oracle.execute_episode(n, sims, e_greedy=0.9, seed=17, game_id=g,
+                                     start_board=oracle.bits_to_board(int(black[g]), int(white[g]), n),
+                                     start_player=int(player[g]))
+        k = int(nm[g])
+        assert [int(a) for a in rec["action"][g][:k]] == [sq8(a, n) for a in ref["moves"]]
+        assert int(rec["winner"][g]) == ref["winner"]
