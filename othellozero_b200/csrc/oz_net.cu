@@ -39,9 +39,17 @@ struct GemmParams {
     int chunks_per_tap;  // Cin / 64 (conv) or num_kb (fc)
     int ntaps_x;         // 3 (conv) or 1 (fc)
     int pad;             // 1: padding='same', 0: 'valid' / fc
-    int nb;              // boards per M tile
+    int nb;              // boards per M tile (full-board box)
     int rows_per_board;  // OH*OW (1 for fc)
-    int rows_valid;      // nb * rows_per_board (<= 128)
+    int rows_valid;      // valid rows of an M tile (<= 128)
+    // split tiles: when nb whole boards leave >= half a board of the 128 rows unused (36-row boards: 3 x 36 = 108),
+    // an M tile is `halves` consecutive HALF boards (7 x 18 = 126 rows) fetched as one whole-board box + one half-board box
+    int split;           // 0 / 1
+    int halves;          // half-boards per tile (2*nb + 1)
+    int half_rows;       // rows of a half board (OH/2 * OW)
+    int half_h;          // OH / 2
+    int tile_den;        // m_tiles = ceil(L * tile_num / tile_den): (1, nb) or (2, halves)
+    int tile_num;
     int n_tiles;         // Nout / BLOCK_N
     int ldc;             // output row stride in elements
     int max_count;
@@ -164,7 +172,8 @@ struct GemmSmem {
 
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
     using S = GemmSmem<BLOCK_N>;
     constexpr int B_STAGE_BYTES = S::B_STAGE_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
@@ -183,7 +192,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int L = *p.count;
     if (L > p.max_count) L = p.max_count;
-    const int m_tiles = (L + p.nb - 1) / p.nb;
+    const int m_tiles = (L * p.tile_num + p.tile_den - 1) / p.tile_den;
     const int num_tiles = m_tiles * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -215,8 +224,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_expect_tx(full_bar(stage), p.a_bytes + (unsigned)B_STAGE_BYTES);
                     const int tap = kb / p.chunks_per_tap, chunk = kb - tap * p.chunks_per_tap;
                     const int ky = tap / p.ntaps_x, kx = tap - ky * p.ntaps_x;
-                    tma_load_4d(sA + stage * A_STAGE_BYTES, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad,
-                                m_tile * p.nb);
+                    const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                    if (!p.split) {
+                        tma_load_4d(dstA, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad, m_tile * p.nb);
+                    } else {
+                        const int hb0 = m_tile * p.halves, b0 = hb0 >> 1;
+                        if (hb0 & 1) {  // lower half of board b0, then nb whole boards
+                            tma_load_4d(dstA, &mapA2, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad + p.half_h, b0);
+                            tma_load_4d(dstA + (uint32_t)(p.half_rows * 128), &mapA, full_bar(stage), chunk * BLOCK_K,
+                                        kx - p.pad, ky - p.pad, b0 + 1);
+                        } else {        // nb whole boards, then the upper half of the next one
+                            tma_load_4d(dstA, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0);
+                            tma_load_4d(dstA + (uint32_t)(p.nb * p.rows_per_board * 128), &mapA2, full_bar(stage),
+                                        chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0 + p.nb);
+                        }
+                    }
                     tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, full_bar(stage), kb * BLOCK_K, n_idx * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -334,6 +356,226 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
 }
 
+// ---- 2-CTA variant: cta_group::2, one 256 x 256 accumulator tile per SM pair ---------------------------------
+// Each CTA of the pair stages its own 128 rows of A and its own 128-row half of the B tile (32 KB per k-block instead
+// of 48 KB: a third less L2->SMEM traffic and half the B operand reads per SM), which also buys a 6-deep ring.  The
+// leader CTA issues tcgen05.mma.cta_group::2 for both; completion is multicast to the barriers of both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = 128 * BLOCK_K * 2;  // this CTA's 128-row half of the 256-row B tile
+struct Gemm2Smem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = STAGES2 * A_STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_B + STAGES2 * B2_STAGE_BYTES;  // full[S], empty[S], tfull[2], tempty[2]
+    static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES2 + 4) * 8;
+    static constexpr int OFF_BIAS = OFF_TMEM + 16;
+    static constexpr int BYTES = OFF_BIAS + 2 * 256 * 4;
+    static constexpr int DYN_BYTES = BYTES + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+                const __grid_constant__ CUtensorMap mapB, const GemmParams p) {
+    using S = Gemm2Smem;
+    constexpr int BLOCK_N = 256;
+    constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + S::OFF_A, sB = base + S::OFF_B, sBar = base + S::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (STAGES2 + s); };
+    auto tfull_bar = [&](int a) { return sBar + 8u * (2 * STAGES2 + a); };
+    auto tempty_bar = [&](int a) { return sBar + 8u * (2 * STAGES2 + 2 + a); };
+    volatile uint32_t* s_tmem = (volatile uint32_t*)(gbase + S::OFF_TMEM);
+    float* s_bias = (float*)(gbase + S::OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    int L = *p.count;
+    if (L > p.max_count) L = p.max_count;
+    const int m_tiles = (L * p.tile_num + p.tile_den - 1) / p.tile_den;
+    const int num_pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }  // 4 epilogue warps x 2 CTAs
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(smem_u32((const void*)s_tmem), TMEM_COLS);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier) =====
+            int stage = 0; uint32_t phase = 0;
+            for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+                const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
+                const int m_tile = 2 * m_pair + (int)rank;
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t fb = mapa_cluster(full_bar(stage), 0);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (p.a_bytes + (unsigned)B2_STAGE_BYTES));
+                    const int tap = kb / p.chunks_per_tap, chunk = kb - tap * p.chunks_per_tap;
+                    const int ky = tap / p.ntaps_x, kx = tap - ky * p.ntaps_x;
+                    const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                    if (!p.split) {
+                        tma_load_4d_2sm(dstA, &mapA, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad, m_tile * p.nb);
+                    } else {
+                        const int hb0 = m_tile * p.halves, b0 = hb0 >> 1;
+                        if (hb0 & 1) {
+                            tma_load_4d_2sm(dstA, &mapA2, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad + p.half_h, b0);
+                            tma_load_4d_2sm(dstA + (uint32_t)(p.half_rows * 128), &mapA, fb, chunk * BLOCK_K, kx - p.pad,
+                                            ky - p.pad, b0 + 1);
+                        } else {
+                            tma_load_4d_2sm(dstA, &mapA, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0);
+                            tma_load_4d_2sm(dstA + (uint32_t)(p.nb * p.rows_per_board * 128), &mapA2, fb, chunk * BLOCK_K,
+                                            kx - p.pad, ky - p.pad, b0 + p.nb);
+                        }
+                    }
+                    tma_load_2d_2sm(sB + stage * B2_STAGE_BYTES, &mapB, fb, kb * BLOCK_K, n_idx * BLOCK_N + (int)rank * 128);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+            constexpr uint32_t idesc = make_idesc(256, BLOCK_N);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < p.num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
+                    const uint64_t bdesc = make_sw128_desc(sB + stage * B2_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_2sm(empty_bar(stage), 3);  // frees the stage in BOTH CTAs
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_2sm(tfull_bar(acc), 3);  // accumulator complete -> both epilogues
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int et = threadIdx.x - 128;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+            const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
+            const int m_tile = 2 * m_pair + (int)rank;
+            float* bias = s_bias + acc * BLOCK_N;
+            for (int i = et; i < BLOCK_N; i += 128) bias[i] = p.bias[n_idx * BLOCK_N + i];
+            epi_bar_sync();
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int r = ew * 32 + lane;
+            const long long grow = (long long)m_tile * p.rows_valid + r;
+            const bool ok = (r < p.rows_valid) && (grow < (long long)L * p.rows_per_board);
+            const uint32_t t_row = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
+            bf16* orow = p.out + grow * p.ldc + (long long)n_idx * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_row + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                if (ok) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], 0.0f);
+                        float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.0f);
+                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // the LEADER's barrier gates the next MMA
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still multicast into it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- conv1 as a table gather -------------------------------------------------------------------------
 // table[pattern][co] = relu(b' + sum_t [s_t==own] W'[t][0][co] + [s_t==opp] W'[t][1][co]), pattern = sum s_t 3^t,
 // t = ky*3+kx (cross-correlation, Keras Conv2D), s = 0 empty / outside the board (zero padding), 1 own, 2 opp.
@@ -445,7 +687,8 @@ PFN_tmapEncodeTiled get_encode_fn() {
 }  // namespace
 
 struct OzLayer {
-    CUtensorMap mapA, mapB;
+    CUtensorMap mapA, mapA2, mapB, mapB2;
+    bool use_2sm = false;
     GemmParams p;
     int block_n;
     int epi;
@@ -568,6 +811,18 @@ static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, in
     p.nb = nb;
     p.rows_per_board = rows_per_board;
     p.rows_valid = nb * rows_per_board;
+    p.tile_num = 1;
+    p.tile_den = nb;
+    static const bool allow_split = !(getenv("OZ_NET_NO_SPLIT") && getenv("OZ_NET_NO_SPLIT")[0] == '1');
+    if (allow_split && ntaps == 3 && (oh % 2) == 0 && (BLOCK_M - nb * rows_per_board) * 2 >= rows_per_board) {
+        p.split = 1;
+        p.half_h = oh / 2;
+        p.half_rows = (oh / 2) * ow;
+        p.halves = 2 * nb + 1;
+        p.rows_valid = p.halves * p.half_rows;
+        p.tile_num = 2;
+        p.tile_den = p.halves;
+    }
     p.ntaps_x = ntaps;
     p.pad = pad;
     p.chunks_per_tap = cin / BLOCK_K;
@@ -581,9 +836,19 @@ static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, in
     p.nsq = net->n * net->n;
     Lr.block_n = block_n;
     Lr.epi = epi;
-    Lr.max_tiles = ((net->Bmax + nb - 1) / nb) * p.n_tiles;
+    Lr.max_tiles = ((net->Bmax * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
     int rc = make_map_A(&Lr.mapA, in, cin, iw, ih, net->Bmax, ow, oh, nb);
     if (rc) return rc;
+    rc = make_map_A(&Lr.mapA2, in, cin, iw, ih, net->Bmax, ow, p.split ? oh / 2 : oh, p.split ? 1 : nb);
+    if (rc) return rc;
+    static const bool allow_2sm = !(getenv("OZ_NET_NO_2SM") && getenv("OZ_NET_NO_2SM")[0] == '1');
+    // measured (B200, 4096 boards): the SM-pair kernel wins on conv2 (0.938 vs 0.955 ms), ties on conv4/fc1/fc2 and loses
+    // on the split-tile conv3 (0.620 vs 0.596 ms) - the step is power-capped, not L2- or SMEM-bound
+    Lr.use_2sm = allow_2sm && epi == EPI_RELU_BF16 && block_n == 256 && !p.split;
+    if (Lr.use_2sm) {
+        rc = make_map_B(&Lr.mapB2, net->w[li], ntaps * ntaps * cin, nout_pad, 128);
+        if (rc) return rc;
+    }
     return make_map_B(&Lr.mapB, net->w[li], ntaps * ntaps * cin, nout_pad, block_n);
 }
 
@@ -624,6 +889,7 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
                                      GemmSmem<128>::DYN_BYTES));
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmSmem<128>::DYN_BYTES));
+        OZ_CUDA(cudaFuncSetAttribute(oz_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem::DYN_BYTES));
         OZ_CUDA(cudaMemsetAsync(net->w[5], 0, 128ull * 512 * 2, st));
         OZ_CUDA(cudaMemsetAsync(net->bias[5], 0, 128 * 4, st));
     }
@@ -714,15 +980,21 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         p.count = count_dev;
         p.max_count = max_count;
         p.pi = pi_dev; p.logits = logits_dev; p.v = v_dev;
-        int tiles = ((max_count + p.nb - 1) / p.nb) * p.n_tiles;
+        int tiles = ((max_count * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
         int grid = tiles < net->sm_count ? tiles : net->sm_count;
         if (grid < 1) grid = 1;
-        if (Lr.epi == EPI_RELU_BF16 && Lr.block_n == 256)
-            oz_gemm_kernel<256, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<256>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+        if (Lr.use_2sm) {
+            int m_tiles = (max_count * p.tile_num + p.tile_den - 1) / p.tile_den;
+            int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
+            int g2 = 2 * pairs < (net->sm_count & ~1) ? 2 * pairs : (net->sm_count & ~1);
+            if (g2 < 2) g2 = 2;
+            oz_gemm2_kernel<<<g2, GEMM_THREADS, Gemm2Smem::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB2, p);
+        } else if (Lr.epi == EPI_RELU_BF16 && Lr.block_n == 256)
+            oz_gemm_kernel<256, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<256>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
         else if (Lr.epi == EPI_RELU_BF16)
-            oz_gemm_kernel<128, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+            oz_gemm_kernel<128, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
         else
-            oz_gemm_kernel<128, EPI_HEADS><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapB, p);
+            oz_gemm_kernel<128, EPI_HEADS><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
         if (tm) cudaEventRecord(ev[2 + li], st);
