@@ -338,7 +338,7 @@ def run_ours(args):
                    "eval_cache_log2": args.eval_cache_log2,
                    "step": (f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
                             if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
-                   "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 336 / 1e9),
+                   "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 432 / 1e9),
                    "starts": "initial position + (game_id % 8) random plies", "parallelism": f"games sharded x{world}"},
         "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
         "net_evals_per_s": tot_nodes / (ms / 1e3), "evals_per_sim": tot_nodes / max(1.0, tot_sims),

@@ -142,6 +142,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Programmatic dependent launch: let the next layer's CTAs start their prologue as ours retire, and make our own
+// first read of the previous layer's output wait for that layer to have completed.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // Shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
@@ -213,9 +217,11 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
+            pdl_wait();  // the activations we are about to read are the previous kernel's output
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n_idx = tile - m_tile * p.n_tiles;
@@ -464,9 +470,11 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier) =====
+            pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
                 const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
@@ -700,6 +708,9 @@ struct OzNet {
     int n = 0, C = 0, Bmax = 0;
     bool loaded = false;
     bool timing = false;
+    bool pdl = true;
+    int timing_every = 16;   // per-layer events on every 16th forward only (an event between two kernels breaks their PDL edge)
+    long forwards = 0;
     int sm_count = 148;
     bf16* table1 = nullptr;
     bf16 *w[6] = {nullptr}; float* bias[6] = {nullptr};  // conv2, conv3, conv4, fc1, fc2, heads
@@ -754,6 +765,10 @@ int oz_net_create(oz_engine* e) {
     net->Bmax = e->cfg.max_games;
     const char* t = getenv("OZ_NET_TIMING");
     net->timing = t && t[0] == '1';
+    const char* pd = getenv("OZ_NET_NO_PDL");
+    net->pdl = !(pd && pd[0] == '1');
+    const char* te = getenv("OZ_NET_TIMING_EVERY");
+    if (te && atoi(te) > 0) net->timing_every = atoi(te);
     int dev = e->cfg.device;
     cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, dev);
     for (int r = 0; r < OzNet::RING; ++r)
@@ -958,7 +973,7 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
     cudaStream_t st = e->stream;
     const int n = net->n, C = net->C, nsq = n * n;
     if (max_count > net->Bmax) max_count = net->Bmax;
-    const bool tm = net->timing;
+    const bool tm = net->timing && (net->forwards++ % net->timing_every) == 0;
     cudaEvent_t* ev = net->ev[net->ev_next];
     if (tm) {
         if (net->ev_used[net->ev_next]) oz_net_harvest(net, net->ev_next);
@@ -983,18 +998,37 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         int tiles = ((max_count * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
         int grid = tiles < net->sm_count ? tiles : net->sm_count;
         if (grid < 1) grid = 1;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.stream = st;
+        cfg.attrs = attr;
+        cfg.numAttrs = net->pdl ? 1 : 0;
+        cudaError_t lerr;
         if (Lr.use_2sm) {
             int m_tiles = (max_count * p.tile_num + p.tile_den - 1) / p.tile_den;
             int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
             int g2 = 2 * pairs < (net->sm_count & ~1) ? 2 * pairs : (net->sm_count & ~1);
             if (g2 < 2) g2 = 2;
-            oz_gemm2_kernel<<<g2, GEMM_THREADS, Gemm2Smem::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB2, p);
-        } else if (Lr.epi == EPI_RELU_BF16 && Lr.block_n == 256)
-            oz_gemm_kernel<256, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<256>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
-        else if (Lr.epi == EPI_RELU_BF16)
-            oz_gemm_kernel<128, EPI_RELU_BF16><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
-        else
-            oz_gemm_kernel<128, EPI_HEADS><<<grid, GEMM_THREADS, GemmSmem<128>::DYN_BYTES, st>>>(Lr.mapA, Lr.mapA2, Lr.mapB, p);
+            cfg.gridDim = dim3(g2);
+            cfg.dynamicSmemBytes = Gemm2Smem::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_gemm2_kernel, Lr.mapA, Lr.mapA2, Lr.mapB2, p);
+        } else if (Lr.epi == EPI_RELU_BF16 && Lr.block_n == 256) {
+            cfg.gridDim = dim3(grid);
+            cfg.dynamicSmemBytes = GemmSmem<256>::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<256, EPI_RELU_BF16>, Lr.mapA, Lr.mapA2, Lr.mapB, p);
+        } else if (Lr.epi == EPI_RELU_BF16) {
+            cfg.gridDim = dim3(grid);
+            cfg.dynamicSmemBytes = GemmSmem<128>::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<128, EPI_RELU_BF16>, Lr.mapA, Lr.mapA2, Lr.mapB, p);
+        } else {
+            cfg.gridDim = dim3(grid);
+            cfg.dynamicSmemBytes = GemmSmem<128>::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_gemm_kernel<128, EPI_HEADS>, Lr.mapA, Lr.mapA2, Lr.mapB, p);
+        }
+        OZ_CUDA(lerr);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
         if (tm) cudaEventRecord(ev[2 + li], st);

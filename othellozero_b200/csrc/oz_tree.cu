@@ -644,8 +644,8 @@ int oz_tree_alloc(oz_engine* e) {
     while ((1ll << log2) < 2ll * e->cfg.nodes_per_game) ++log2;
     e->table_log2 = log2;
     P.table_log2 = log2;
-    // average node: 48 + 24*k bytes; k averages ~8.4 (8x8), allow 12 and never less than one max-size node
-    u64 stride = (u64)e->cfg.nodes_per_game * (48 + 24 * 12);
+    // average node: 48 + 24*k bytes; k averages ~8.4 on 8x8 (max seen 20): budget 16 children per node
+    u64 stride = (u64)e->cfg.nodes_per_game * (48 + 24 * 16);
     if (stride < 4096) stride = 4096;
     stride = (stride + 255) & ~255ull;
     e->arena_stride = stride;

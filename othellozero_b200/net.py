@@ -147,8 +147,15 @@ class B200NNet:
         pi, v = self.predict_batch(own, opp)
         return pi[0].reshape(self.board_size_x, self.board_size_y), np.float32(v[0])
 
-    def train(self, examples, verbose=None):
-        raise NotImplementedError("training (Net/NNet.py:53-68) is outside the self-play hot path; see DESIGN.md")
+    def train(self, examples, verbose=None, epochs: int = 10, batch_size: int = 32, lr: float = 1e-3,
+              dropout: float = 0.3):
+        """Net/NNet.py:53-68 with the compile settings of Net/OthelloNN.py:55-56 (PyTorch autograd; see train.py).
+        The trained weights are folded and re-loaded onto the device tower."""
+        from .train import train_blob
+        blob, history = train_blob(self.blob, examples, self.board_size_x, self.channels, epochs=epochs,
+                                   batch_size=batch_size, lr=lr, dropout=dropout, verbose=bool(verbose))
+        self.set_weights(blob)
+        return history
 
     def save_checkpoint(self, filepath):
         np.savez(filepath, blob=self.blob, board_size=self.board_size_x, channels=self.channels)
