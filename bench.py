@@ -291,6 +291,12 @@ def run_ours(args):
     # ---- e2e: complete games through the public API with HOST buffers (copies inside) ----------------------------
     e2e = None
     if not args.no_e2e:
+        # cold start: fresh games (other ids / start positions) and an EMPTY evaluation cache (reloading the weights
+        # clears it), so nothing evaluated during the timed region above can be reused here
+        if mode == E.PRIOR_NET:
+            eng.load_weights_from_tensor(wt, C)
+        sb, sw, sp = synthetic_starts(E, G, args.seed + 1, (1 << 24) + first_id, local)
+        ids = np.arange((1 << 24) + first_id, (1 << 24) + first_id + G, dtype=np.uint64)
         barrier()
         t0 = time.perf_counter()
         eng.selfplay_begin(args.e2e_games, sims, 1.0, 0.9, args.e2e_moves, sb[:args.e2e_games], sw[:args.e2e_games],
