@@ -76,13 +76,9 @@ def test_host_prior_episode_golden(E, golden_episodes, name):
 
     e = E.Engine(n, max_games=1, nodes_per_game=rec["sims"] * (n * n) + 64, prior_mode=E.PRIOR_HOST, c_puct=rec["c"])
     board = oracle.initial_board(n)
-    game = dict(board=board, player=0)
     b, w = oracle.board_to_bits(board)
     e.reset(1, [b], [w], [0])
     moves = []
-    lib = oracle.lib()
-    import ctypes as C
-    g = np.zeros(1)  # placeholder to keep flake quiet
     cur = oracle.as_board(board).copy()
     player = 0
     for p, exp_vis in enumerate(rec["visits"]):
