@@ -65,7 +65,8 @@ typedef struct oz_engine_config {
     int32_t log_visits;      /* keep per-move root visit counts of self-play games (tests) */
     int32_t eval_cache_log2; /* OZ_PRIOR_NET: log2(entries) of the cross-game evaluation cache (272 B/entry); 0 = off.
                                 Identical positions are evaluated once; results are unchanged. */
-    int32_t reserved;
+    int32_t vl_width;        /* > 1: up to vl_width simulations of a game in flight per step (virtual loss); visit counts
+                                then differ from the sequential reference by design. 0/1 = sequential, bit-exact. */
     double c_puct;           /* degree_exploration (MCTS/__init__.py:27,168-170) */
     uint64_t seed;           /* engine RNG seed (epsilon-greedy, synthetic starts) */
 } oz_engine_config;

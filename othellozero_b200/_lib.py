@@ -16,7 +16,7 @@ GAME_IDLE, GAME_ACTIVE, GAME_WAIT_LEAF, GAME_FINISHED, GAME_POOL_FULL = 0, 1, 2,
 class EngineConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("board_size", C.c_int32), ("max_games", C.c_int32),
                 ("nodes_per_game", C.c_int32), ("prior_mode", C.c_int32), ("log_visits", C.c_int32),
-                ("eval_cache_log2", C.c_int32), ("reserved", C.c_int32), ("c_puct", C.c_double), ("seed", C.c_uint64)]
+                ("eval_cache_log2", C.c_int32), ("vl_width", C.c_int32), ("c_puct", C.c_double), ("seed", C.c_uint64)]
 
 
 u64p = C.POINTER(C.c_uint64)

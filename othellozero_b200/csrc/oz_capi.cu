@@ -58,6 +58,7 @@ extern "C" int oz_engine_create(const oz_engine_config* cfg, oz_engine** out) {
                cfg->nodes_per_game);
     OZ_REQUIRE(cfg->prior_mode >= OZ_PRIOR_HASH && cfg->prior_mode <= OZ_PRIOR_NET, "bad prior_mode %d", cfg->prior_mode);
     OZ_REQUIRE(cfg->prior_mode != OZ_PRIOR_NET || cfg->board_size >= 6, "the network needs board_size 6 or 8");
+    OZ_REQUIRE(cfg->vl_width >= 0 && cfg->vl_width <= 64, "vl_width out of range: %d", cfg->vl_width);
     int ndev = 0;
     int rc = oz_device_count(&ndev);
     if (rc) return rc;
@@ -160,7 +161,7 @@ static int read_leaf_count(oz_engine* e, int* n) {
 
 // Evaluate the pending leaf batch with the device network (count stays on the device).
 static int eval_leaves_net(oz_engine* e) {
-    int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games, e->leaf_pi, e->leaf_logits,
+    int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, e->leaf_logits,
                             e->leaf_v);
     if (rc) return rc;
     return oz_tree_cache_publish(e);
@@ -404,7 +405,7 @@ extern "C" int oz_net_load_weights_dev(oz_engine* e, const float* blob_dev, int6
 extern "C" int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint64_t* opp, int32_t n, float* pi,
                                   float* logits, float* v) {
     OZ_REQUIRE(e && own && opp && pi && v, "null argument");
-    OZ_REQUIRE(n >= 1 && n <= e->cfg.max_games, "n %d out of range (max_games %d)", n, e->cfg.max_games);
+    OZ_REQUIRE(n >= 1 && n <= e->max_leaves, "n %d out of range (capacity %d)", n, e->max_leaves);
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     e->h_pinned[3] = n;
     int* cnt = e->tp.leaf_count + 1;
@@ -418,7 +419,7 @@ extern "C" int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint6
 extern "C" int oz_net_forward_host(oz_engine* e, const uint64_t* own, const uint64_t* opp, int32_t n, float* pi,
                                    float* logits, float* v) {
     OZ_REQUIRE(e && own && opp && pi && v, "null argument");
-    OZ_REQUIRE(n >= 1 && n <= e->cfg.max_games, "n %d out of range (max_games %d)", n, e->cfg.max_games);
+    OZ_REQUIRE(n >= 1 && n <= e->max_leaves, "n %d out of range (capacity %d)", n, e->max_leaves);
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     const int nsq = e->tp.nsq;
     OZ_CUDA(cudaMemcpyAsync(e->tp.leaf_own, own, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));

@@ -40,13 +40,15 @@ struct __align__(16) OzNodeHdr {
     u64 qf32;      // bit j: Q[j] currently has numpy float32 type (else python float / int 0)
     int ns;        // _Ns
     int k;
-    int pad0, pad1;
+    int vns;       // in-flight (virtual) visits through this node; 0 outside a virtual-loss wave
+    int pad1;
 };
 static_assert(sizeof(OzNodeHdr) == 48, "node header layout");
 
 constexpr int OZ_CH_UNKNOWN = -1;   // edge never traversed
 constexpr int OZ_CH_TERM_NEG = -2;  // child is terminal, simulate() returns -1
 constexpr int OZ_CH_TERM_POS = -3;  // child is terminal, simulate() returns +1
+constexpr int OZ_CH_PENDING = -4;   // leaf emitted by the current virtual-loss wave, not expanded yet
 constexpr int OZ_MAX_DEPTH = 64;
 
 struct OzTreeParams {
@@ -63,8 +65,10 @@ struct OzTreeParams {
     int* status; int* root_node; int* sims_left; int* ply; u64* game_id; int* winner;
     // pending leaf (WAIT_LEAF)
     u64* pend_own; u64* pend_opp; u64* pend_legal;
-    int* pend_parent; int* pend_edge; int* pend_depth; int* pend_leaf;
-    u32* path_node; u32* path_edge;  // [G][64]
+    int* pend_parent; int* pend_edge; int* pend_depth; int* pend_leaf;  // [G][vl_width]
+    int* pend_count;                                                     // [G] leaves of the current wave
+    int vl_width;                                                        // 1 = sequential (bit-exact) mode
+    u32* path_node; u32* path_edge;  // [G][vl_width][64]
     // pools
     unsigned char* arena; u64 arena_stride;  // bytes per game
     u32* bump;                                // next free offset (16-byte units) per game
@@ -95,6 +99,7 @@ struct oz_engine {
     u64 arena_stride = 0;
     u64 launches = 0;
     size_t cache_entries = 0;
+    int max_leaves = 0;        // max_games * vl_width: capacity of the leaf batch and of the network
     // device allocations (freed in destroy)
     void* allocs[64];
     int n_allocs = 0;

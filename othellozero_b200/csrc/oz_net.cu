@@ -762,7 +762,7 @@ int oz_net_create(oz_engine* e) {
     if (e->cfg.prior_mode != OZ_PRIOR_NET) return OZ_OK;
     OzNet* net = new OzNet();
     net->n = e->cfg.board_size;
-    net->Bmax = e->cfg.max_games;
+    net->Bmax = e->cfg.max_games * (e->cfg.vl_width > 1 ? e->cfg.vl_width : 1);
     const char* t = getenv("OZ_NET_TIMING");
     net->timing = t && t[0] == '1';
     const char* pd = getenv("OZ_NET_NO_PDL");

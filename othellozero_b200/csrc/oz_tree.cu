@@ -17,6 +17,13 @@
 //            (MCTS/__init__.py:68-71), sign flip per ply
 //   move     visit counts -> action (first arg-max or epsilon-random), example record, OthelloGame.play
 //            (training.py:48-67)
+//
+// Virtual-loss waves (vl_width > 1, BASELINE configs[3]): the same warp runs up to vl_width descents per step, each
+// leaving a virtual loss (an in-flight visit counted as a loss) on its path so that the next descent of the wave goes
+// elsewhere; the leaves of a wave are evaluated together and backed up (virtual losses removed) in emission order at
+// the start of the next step.  This fills the leaf batch with few games but changes visit counts relative to the
+// sequential reference BY DESIGN; vl_width = 1 is the bit-exact mode and executes exactly the sequential code path.
+// The in-flight count of an edge lives in the top 8 bits of its N word, the node's total in the header's `vns`.
 #include "oz_engine.cuh"
 
 using namespace ozbb;
@@ -85,7 +92,10 @@ __device__ __forceinline__ void path_set(SimPath& p, int lane, int depth, u32 no
 
 // MCTS/__init__.py:68-70 for every edge of the path, lanes in parallel (a path never repeats a node).
 // (is_int, iv, fv) = the value handed to the DEEPEST edge; it alternates sign going up (:71).
-__device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, int depth, bool is_int, int iv, float fv) {
+constexpr int N_MASK = 0x00FFFFFF;  // low 24 bits of an N word = visits, high 8 bits = virtual (in-flight) visits
+
+__device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, int depth, bool is_int, int iv, float fv,
+                            bool vl) {
     for (int t = lane; t < depth; t += 32) {
         u32 noff = (t < 32) ? p.n0 : p.n1;
         u32 e = (t < 32) ? p.e0 : p.e1;
@@ -96,7 +106,9 @@ __device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, in
         int k = h->k;
         double* Q = node_Q(h, k);
         int* N = node_N(h, k);
-        int nn = N[e];
+        const int nraw = N[e];
+        const int nn = nraw & N_MASK;
+        const int vn = (int)((unsigned)nraw >> 24);
         double q = Q[e];
         u64 bit = 1ull << e;
         bool f32 = (h->qf32 & bit) != 0ull;
@@ -123,9 +135,22 @@ __device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, in
             q = (double)__fdiv_rn(s, (float)(nn + 1));
         }
         Q[e] = q;
-        N[e] = nn + 1;
+        N[e] = (nn + 1) | ((vl ? vn - 1 : vn) << 24);
         if (f32) h->qf32 |= bit;
         h->ns += 1;
+        if (vl) h->vns -= 1;
+    }
+    __syncwarp();
+}
+
+// A descent of a virtual-loss wave that ran into a leaf already in flight: take its virtual losses back.
+__device__ void revert_path(unsigned char* arena, const SimPath& p, int lane, int depth) {
+    for (int t = lane; t < depth; t += 32) {
+        u32 noff = (t < 32) ? p.n0 : p.n1;
+        u32 e = (t < 32) ? p.e0 : p.e1;
+        OzNodeHdr* h = node_at(arena, noff);
+        node_N(h, h->k)[e] -= (1 << 24);
+        h->vns -= 1;
     }
     __syncwarp();
 }
@@ -147,14 +172,25 @@ struct Pending {
 // lane+32), followed by the backup of -v.  Returns false when the node pool is exhausted.
 __device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, unsigned char* arena, u64* table,
                                   const Pending& pd, float pi_lo, float pi_hi, float v, double* sa,
-                                  const SimPath& path) {
+                                  const SimPath& path, bool vl, bool* created) {
     const int n = P.n, nsq = P.nsq;
     int k = popc(pd.legal);
     u32 units = node_units(k);
     u32 off = P.bump[slot];
     u32 ins;
     int found = table_find(table, P.table_log2, arena, pd.own, pd.opp, lane, &ins);
-    (void)found;
+    *created = found < 0;
+    if (found >= 0) {
+        // only in a virtual-loss wave: two edges of the wave led to the same new position; the first one created the
+        // node, this one just links to it and backs its (identical) value up
+        if (lane == 0 && pd.parent >= 0) {
+            OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
+            node_child(ph, ph->k)[pd.pedge] = found;
+        }
+        __syncwarp();
+        backup_path(arena, path, lane, pd.depth, false, 0, -v, vl);
+        return true;
+    }
     if (((u64)off + units) * 16ull > P.arena_stride || ins == 0xffffffffu) return false;
 
     // numpy order: a = pi(f32) * mask(f64) over the flat (N,N) array (othelo_mcts.py:69-73)
@@ -201,7 +237,7 @@ __device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, uns
     }
     if (lane == 0) {
         h->own = pd.own; h->opp = pd.opp; h->legal = pd.legal; h->qf32 = 0ull;
-        h->ns = 0; h->k = k; h->pad0 = 0; h->pad1 = 0;
+        h->ns = 0; h->k = k; h->vns = 0; h->pad1 = 0;
         table[ins] = ((u64)(u32)(key_hash(pd.own, pd.opp) >> 32) << 32) | (u64)(off + 1u);
         P.bump[slot] = off + units;
         if (pd.parent >= 0) {
@@ -212,7 +248,7 @@ __device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, uns
         }
     }
     __syncwarp();
-    backup_path(arena, path, lane, pd.depth, false, 0, -v);  // MCTS:57 returns -v to the parent
+    backup_path(arena, path, lane, pd.depth, false, 0, -v, vl);  // MCTS:57 returns -v to the parent
     return true;
 }
 
@@ -326,38 +362,50 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
     SimPath path{0, 0, 0, 0};
     Pending pd;
 
+    const int V = P.vl_width;
+    const bool vl = V > 1;
     if (status == OZ_GAME_WAIT_LEAF) {
-        pd.own = P.pend_own[slot]; pd.opp = P.pend_opp[slot]; pd.legal = P.pend_legal[slot];
-        pd.parent = P.pend_parent[slot]; pd.pedge = P.pend_edge[slot]; pd.depth = P.pend_depth[slot];
-        int li = P.pend_leaf[slot];
-        const u32* pn = P.path_node + (size_t)slot * OZ_MAX_DEPTH;
-        const u32* pe = P.path_edge + (size_t)slot * OZ_MAX_DEPTH;
-        if (lane < pd.depth) { path.n0 = pn[lane]; path.e0 = pe[lane]; }
-        if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
-        // priors for this lane's two squares, row layout r*n+c with row stride 64
-        float pi_lo = 0.f, pi_hi = 0.f;
-        {
-            int r = lane >> 3, c = lane & 7;
-            if (r < n && c < n) pi_lo = P.leaf_pi[(size_t)li * 64 + r * n + c];
-            r += 4;
-            if (r < n && c < n) pi_hi = P.leaf_pi[(size_t)li * 64 + r * n + c];
+        // finish the simulations whose leaves have just been evaluated, in emission order (MCTS/__init__.py:44-57,67-71)
+        const int npend = P.pend_count[slot];
+        for (int i = 0; i < npend; ++i) {
+            const size_t pi_ = (size_t)slot * V + i;
+            pd.own = P.pend_own[pi_]; pd.opp = P.pend_opp[pi_]; pd.legal = P.pend_legal[pi_];
+            pd.parent = P.pend_parent[pi_]; pd.pedge = P.pend_edge[pi_]; pd.depth = P.pend_depth[pi_];
+            const int li = P.pend_leaf[pi_];
+            const u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
+            const u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
+            if (lane < pd.depth) { path.n0 = pn[lane]; path.e0 = pe[lane]; }
+            if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
+            // priors for this lane's two squares, row layout r*n+c with row stride 64
+            float pi_lo = 0.f, pi_hi = 0.f;
+            {
+                int r = lane >> 3, c = lane & 7;
+                if (r < n && c < n) pi_lo = P.leaf_pi[(size_t)li * 64 + r * n + c];
+                r += 4;
+                if (r < n && c < n) pi_hi = P.leaf_pi[(size_t)li * 64 + r * n + c];
+            }
+            const float v = P.leaf_v[li];
+            bool created;
+            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
+                if (lane == 0) P.status[slot] = OZ_GAME_POOL_FULL;
+                return;
+            }
+            c_nodes += created ? 1 : 0;
+            c_trans += created ? 0 : 1;
+            ++c_sims;
+            --sims_left;
         }
-        float v = P.leaf_v[li];
-        if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
-            if (lane == 0) P.status[slot] = OZ_GAME_POOL_FULL;
-            return;
-        }
-        ++c_nodes; ++c_sims;
-        --sims_left;
         status = OZ_GAME_ACTIVE;
     }
+    int inflight = 0;  // leaves parked by this launch (the current wave)
 
     u64 black = P.black[slot], white = P.white[slot];
     int player = P.player[slot];
     int ply = P.ply[slot];
 
     while (true) {
-        if (sims_left <= 0) {
+        if (sims_left - inflight <= 0) {
+            if (inflight > 0) { status = OZ_GAME_WAIT_LEAF; break; }
             if (!P.selfplay) { status = OZ_GAME_IDLE; break; }
             // ---- move transition: training.py:45-67 --------------------------------------------------
             u64 own = player ? white : black, opp = player ? black : white;
@@ -369,7 +417,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             // visit counts by child slot; first arg-max == np.argwhere(policy == policy.max())[0]
             double best = -1.0; int bj = 1 << 20;
             for (int j = lane; j < k; j += 32) {
-                double cnt = (double)Np[j];
+                double cnt = (double)(Np[j] & N_MASK);
                 if (cnt > best) { best = cnt; bj = j; }
             }
             warp_argmax(best, bj);
@@ -388,7 +436,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         int s = lane + 32 * half;
-                        int cnt = ((legal >> s) & 1ull) ? Np[popc(legal & ((1ull << s) - 1ull))] : 0;
+                        int cnt = ((legal >> s) & 1ull) ? (Np[popc(legal & ((1ull << s) - 1ull))] & N_MASK) : 0;
                         P.rec_visits[ri * 64 + s] = cnt;
                     }
                 }
@@ -420,6 +468,8 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             continue;
         }
 
+        if (inflight >= V) { status = OZ_GAME_WAIT_LEAF; break; }  // wave is full: wait for the evaluator
+
         // ---- one simulation: MCTS.simulate from the canonical root (othelo_mcts.py:22-26) -----------
         int node = P.root_node[slot];
         int depth = 0;
@@ -444,20 +494,29 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             const int ns = h->ns;
             const double* Pp = node_P(h);
             const double* Qp = node_Q(h, k);
-            const int* Np = node_N(h, k);
+            int* Np = node_N(h, k);
             int* Cp = node_child(h, k);
-            const double sq_ns = __dsqrt_rn((double)ns);
+            const double sq_ns = __dsqrt_rn((double)(ns + h->vns));
             double bu = -1.0e300; int bj = 1 << 20;
             for (int j = lane; j < k; j += 32) {
-                double bound = __ddiv_rn(sq_ns, (double)(1 + Np[j]));
-                double u = __dadd_rn(Qp[j], __dmul_rn(__dmul_rn(P.c, Pp[j]), bound));
+                const int nraw = Np[j];
+                const int nj = nraw & N_MASK, vn = (int)((unsigned)nraw >> 24);
+                double q = Qp[j];
+                if (vn) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nj, q), -(double)vn), (double)(nj + vn));  // in-flight = losses
+                double bound = __ddiv_rn(sq_ns, (double)(1 + nj + vn));
+                double u = __dadd_rn(q, __dmul_rn(__dmul_rn(P.c, Pp[j]), bound));
                 if (u > bu) { bu = u; bj = j; }
             }
             warp_argmax(bu, bj);
             path_set(path, lane, depth, (u32)node, (u32)bj);
             ++depth;
+            if (vl) {  // leave a virtual loss on the chosen edge for the rest of the wave
+                if (lane == 0) { Np[bj] += (1 << 24); h->vns += 1; }
+                __syncwarp();
+            }
             int ch = Cp[bj];
             if (ch >= 0) { node = ch; continue; }
+            if (ch == OZ_CH_PENDING) { outcome = 3; break; }  // that leaf is already in flight in this wave
             if (ch == OZ_CH_TERM_NEG || ch == OZ_CH_TERM_POS) {
                 term_val = (ch == OZ_CH_TERM_POS) ? 1 : -1;
                 outcome = 1;
@@ -491,8 +550,13 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         if (depth > c_depth) c_depth = depth;
         __syncwarp();
 
+        if (outcome == 3) {
+            revert_path(arena, path, lane, depth);
+            status = OZ_GAME_WAIT_LEAF;  // inflight > 0 here: pending edges only exist inside a wave
+            break;
+        }
         if (outcome == 1) {
-            backup_path(arena, path, lane, depth, true, term_val, (float)term_val);
+            backup_path(arena, path, lane, depth, true, term_val, (float)term_val, vl);
             ++c_term; ++c_sims;
             --sims_left;
             continue;
@@ -502,7 +566,8 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             u64 key = sm64(pd.own ^ sm64(pd.opp));
             float pi_lo = hash_pi(key, lane), pi_hi = hash_pi(key, lane + 32);
             float v = hash_v(key);
-            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
+            bool created;
+            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
                 status = OZ_GAME_POOL_FULL;
                 break;
             }
@@ -522,7 +587,8 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
                 if (r < n && c < n) pi_lo = row[r * n + c];
                 if (r + 4 < n && c < n) pi_hi = row[(r + 4) * n + c];
                 const float v = P.cache_v[cidx];
-                if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path)) {
+                bool created;
+                if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
                     status = OZ_GAME_POOL_FULL;
                     break;
                 }
@@ -547,21 +613,30 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
                 }
             }
         }
-        if (lane == 0) {
-            P.pend_own[slot] = pd.own; P.pend_opp[slot] = pd.opp; P.pend_legal[slot] = pd.legal;
-            P.pend_parent[slot] = pd.parent; P.pend_edge[slot] = pd.pedge; P.pend_depth[slot] = pd.depth;
-            P.pend_leaf[slot] = li;
+        {
+            const size_t pi_ = (size_t)slot * V + inflight;
+            if (lane == 0) {
+                P.pend_own[pi_] = pd.own; P.pend_opp[pi_] = pd.opp; P.pend_legal[pi_] = pd.legal;
+                P.pend_parent[pi_] = pd.parent; P.pend_edge[pi_] = pd.pedge; P.pend_depth[pi_] = pd.depth;
+                P.pend_leaf[pi_] = li;
+                if (vl && pd.parent >= 0) {  // later descents of this wave must not emit the same leaf again
+                    OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
+                    node_child(ph, ph->k)[pd.pedge] = OZ_CH_PENDING;
+                }
+            }
+            u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
+            u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
+            if (lane < pd.depth) { pn[lane] = path.n0; pe[lane] = path.e0; }
+            if (lane + 32 < pd.depth) { pn[lane + 32] = path.n1; pe[lane + 32] = path.e1; }
+            __syncwarp();
         }
-        u32* pn = P.path_node + (size_t)slot * OZ_MAX_DEPTH;
-        u32* pe = P.path_edge + (size_t)slot * OZ_MAX_DEPTH;
-        if (lane < pd.depth) { pn[lane] = path.n0; pe[lane] = path.e0; }
-        if (lane + 32 < pd.depth) { pn[lane + 32] = path.n1; pe[lane + 32] = path.e1; }
-        status = OZ_GAME_WAIT_LEAF;
-        break;
+        ++inflight;
+        if (pd.parent < 0) { status = OZ_GAME_WAIT_LEAF; break; }  // the root itself: nothing else can run before it exists
     }
 
     if (lane == 0) {
         P.status[slot] = status;
+        P.pend_count[slot] = inflight;
         P.sims_left[slot] = sims_left;
         P.black[slot] = black; P.white[slot] = white; P.player[slot] = player; P.ply[slot] = ply;
         if (c_sims) atomicAdd(&P.counters[0], c_sims);
@@ -591,9 +666,9 @@ __global__ void tree_visits_kernel(const OzTreeParams P, int* __restrict__ visit
         OzNodeHdr* h = node_at(arena, (u32)root);
         u64 legal = h->legal;
         const int* Np = node_N(h, h->k);
-        if ((legal >> lane) & 1ull) v0 = Np[popc(legal & ((1ull << lane) - 1ull))];
-        if ((legal >> (lane + 32)) & 1ull) v1 = Np[popc(legal & ((1ull << (lane + 32)) - 1ull))];
-        nsv = h->ns;
+        if ((legal >> lane) & 1ull) v0 = Np[popc(legal & ((1ull << lane) - 1ull))] & N_MASK;
+        if ((legal >> (lane + 32)) & 1ull) v1 = Np[popc(legal & ((1ull << (lane + 32)) - 1ull))] & N_MASK;
+        nsv = h->ns | (h->vns << 24);  // vns must be 0 whenever no wave is in flight
     }
     visits[(size_t)slot * 64 + lane] = v0;
     visits[(size_t)slot * 64 + lane + 32] = v1;
@@ -621,7 +696,7 @@ __global__ void tree_root_stats_kernel(const OzTreeParams P, int slot, double* _
                 int k = h->k;
                 qq = node_Q(h, k)[j];
                 pp = node_P(h)[j];
-                int nn = node_N(h, k)[j];
+                int nn = node_N(h, k)[j] & N_MASK;
                 tt = (nn == 0) ? 0 : (((h->qf32 >> j) & 1ull) ? 2 : 1);
             }
         }
@@ -633,6 +708,10 @@ __global__ void tree_root_stats_kernel(const OzTreeParams P, int slot, double* _
 int oz_tree_alloc(oz_engine* e) {
     const int G = e->cfg.max_games;
     OzTreeParams& P = e->tp;
+    const int V = e->cfg.vl_width > 1 ? e->cfg.vl_width : 1;
+    P.vl_width = V;
+    e->max_leaves = G * V;
+    const size_t GV = (size_t)G * V;
     P.n = e->cfg.board_size;
     P.nsq = P.n * P.n;
     P.full = full_mask(P.n);
@@ -654,11 +733,11 @@ int oz_tree_alloc(oz_engine* e) {
 #define A(field, T, count) if ((rc = oz_dev_alloc<T>(e, (T**)&P.field, (size_t)(count)))) return rc;
     A(black, u64, G) A(white, u64, G) A(player, int, G) A(status, int, G) A(root_node, int, G)
     A(sims_left, int, G) A(ply, int, G) A(game_id, u64, G) A(winner, int, G)
-    A(pend_own, u64, G) A(pend_opp, u64, G) A(pend_legal, u64, G) A(pend_parent, int, G) A(pend_edge, int, G)
-    A(pend_depth, int, G) A(pend_leaf, int, G)
-    A(path_node, u32, (size_t)G * OZ_MAX_DEPTH) A(path_edge, u32, (size_t)G * OZ_MAX_DEPTH)
+    A(pend_own, u64, GV) A(pend_opp, u64, GV) A(pend_legal, u64, GV) A(pend_parent, int, GV) A(pend_edge, int, GV)
+    A(pend_depth, int, GV) A(pend_leaf, int, GV) A(pend_count, int, G)
+    A(path_node, u32, GV * OZ_MAX_DEPTH) A(path_edge, u32, GV * OZ_MAX_DEPTH)
     A(arena, unsigned char, (size_t)G * stride) A(bump, u32, G) A(table, u64, (size_t)G << log2)
-    A(leaf_own, u64, G) A(leaf_opp, u64, G) A(leaf_count, int, 4)
+    A(leaf_own, u64, GV) A(leaf_opp, u64, GV) A(leaf_count, int, 4)
     A(rec_black, u64, (size_t)G * 64) A(rec_white, u64, (size_t)G * 64) A(rec_action, unsigned char, (size_t)G * 64)
     A(rec_player, unsigned char, (size_t)G * 64)
     A(counters, u64, 8) A(n_active, int, 4)
@@ -670,19 +749,20 @@ int oz_tree_alloc(oz_engine* e) {
         if (lg > 28) lg = 28;
         const size_t entries = (size_t)1 << lg;
         A(cache_tags, u64, entries) A(cache_keys, u64, entries * 2) A(cache_leaf, int, entries)
-        A(cache_pi, float, entries * 64) A(cache_v, float, entries) A(leaf_cache_idx, int, G)
+        A(cache_pi, float, entries * 64) A(cache_v, float, entries) A(leaf_cache_idx, int, GV)
         P.cache_log2_buckets = lg - 3;
         e->cache_entries = entries;
         OZ_CUDA(cudaMemsetAsync(P.cache_tags, 0, entries * sizeof(u64), e->stream));
     }
 #undef A
-    if ((rc = oz_dev_alloc<float>(e, &e->leaf_pi, (size_t)G * 64))) return rc;
-    if ((rc = oz_dev_alloc<float>(e, &e->leaf_logits, (size_t)G * 64))) return rc;
-    if ((rc = oz_dev_alloc<float>(e, &e->leaf_v, (size_t)G))) return rc;
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_pi, GV * 64))) return rc;
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_logits, GV * 64))) return rc;
+    if ((rc = oz_dev_alloc<float>(e, &e->leaf_v, GV))) return rc;
     P.leaf_pi = e->leaf_pi;
     P.leaf_v = e->leaf_v;
     OZ_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(u64), e->stream));
     OZ_CUDA(cudaMemsetAsync(P.status, 0, G * sizeof(int), e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.pend_count, 0, G * sizeof(int), e->stream));
     OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, 4 * sizeof(int), e->stream));
     OZ_CUDA(cudaMemsetAsync(P.n_active, 0, 4 * sizeof(int), e->stream));
     return OZ_OK;
@@ -706,6 +786,7 @@ __global__ void tree_init_slots_kernel(const OzTreeParams P, int n_games, const 
             P.winner[g] = -1;
         }
         P.status[g] = OZ_GAME_IDLE;
+        P.pend_count[g] = 0;
         P.root_node[g] = -1;
         P.sims_left[g] = 0;
     } else if (clear) {
@@ -801,7 +882,7 @@ int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int
 int oz_tree_cache_publish(oz_engine* e) {
     OzTreeParams& P = e->tp;
     if (!P.cache_tags) return OZ_OK;
-    cache_publish_kernel<<<(P.G + 7) / 8, 256, 0, e->stream>>>(P);
+    cache_publish_kernel<<<(P.G * P.vl_width + 7) / 8, 256, 0, e->stream>>>(P);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
     return OZ_OK;

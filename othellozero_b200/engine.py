@@ -63,7 +63,7 @@ class Engine:
 
     def __init__(self, board_size: int = 8, max_games: int = 1, nodes_per_game: int = 8192,
                  prior_mode: int = PRIOR_HASH, c_puct: float = 1.0, seed: int = 0, device: int = 0,
-                 log_visits: bool = False, eval_cache_log2: int = 0):
+                 log_visits: bool = False, eval_cache_log2: int = 0, vl_width: int = 1):
         self._L = _lib.load()
         self.board_size = board_size
         self.nsq = board_size * board_size
@@ -71,8 +71,10 @@ class Engine:
         self.prior_mode = prior_mode
         self.device = device
         self.log_visits = log_visits
+        self.vl_width = max(1, int(vl_width))
+        self.max_leaves = max_games * self.vl_width
         cfg = _lib.EngineConfig(device, board_size, max_games, nodes_per_game, prior_mode, int(log_visits),
-                                int(eval_cache_log2), 0, float(c_puct), seed & M64)
+                                int(eval_cache_log2), int(vl_width), float(c_puct), seed & M64)
         h = C.c_void_p()
         check(self._L.oz_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
