@@ -205,7 +205,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
     n, C, sims, G = 8, args.channels, args.sims, args.games
-    STEPS_PER_MOVE = sims
+    STEPS_PER_MOVE = (sims + max(1, args.vl) - 1) // max(1, args.vl)
 
     def barrier():
         if world > 1:
@@ -217,7 +217,7 @@ def run_ours(args):
 
     mode = E.PRIOR_NET if args.workload == "selfplay" else E.PRIOR_HASH
     eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
-                   device=local, eval_cache_log2=args.eval_cache_log2 if mode == E.PRIOR_NET else 0)
+                   device=local, eval_cache_log2=args.eval_cache_log2 if mode == E.PRIOR_NET else 0, vl_width=args.vl)
     if mode == E.PRIOR_NET:
         # C1: rank 0 owns the weights, everyone else receives them over NCCL and folds them on device
         nfl = oznet.blob_size(n, C)
@@ -337,11 +337,12 @@ def run_ours(args):
         "metric": "mcts_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if mode == E.PRIOR_NET else "f64", "data": "synthetic",
-        "config": {"workload": ("8x8 self-play, 100 sims/move, %d concurrent games per GPU, random-init OthelloNNet "
-                                "C=%d bf16 leaf eval (BASELINE.json configs[2])" % (G, C)) if mode == E.PRIOR_NET else
+        "config": {"workload": ("8x8 self-play, %d sims/move, %d concurrent games per GPU, random-init OthelloNNet "
+                                "C=%d bf16 leaf eval (BASELINE.json configs[%d])" % (sims, G, C, 2 if args.vl <= 1 else 3))
+                   if mode == E.PRIOR_NET else
                    "8x8 self-play tree+rules only, closed-form hash priors (no network)",
                    "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
-                   "eval_cache_log2": args.eval_cache_log2,
+                   "eval_cache_log2": args.eval_cache_log2, "vl_width": args.vl,
                    "step": (f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
                             if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 432 / 1e9),
@@ -356,7 +357,7 @@ def run_ours(args):
         out["nccl"] = {"weights_broadcast_floats": int(oznet.blob_size(n, C)) if mode == E.PRIOR_NET else 0,
                        "examples_gathered": gathered}
     if mode == E.PRIOR_NET:
-        avg_leaves = (d_evals / max(1, tree_steps))
+        avg_leaves = (d_evals / max(1, tree_steps))  # boards per forward
         conv2_ms = float(lt[1])
         achieved = FLOP_CONV2_PER_BOARD_8 * (C / 512.0) ** 2 * avg_leaves / (conv2_ms * 1e-3) / 1e12 if conv2_ms > 0 else 0.0
         peak = peaks["bf16_sustained"]
@@ -459,6 +460,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=1)
     ap.add_argument("--eval-cache-log2", type=int, default=24)
+    ap.add_argument("--vl", type=int, default=1, help="virtual-loss wave width (configs[3]); 1 = sequential, bit-exact")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

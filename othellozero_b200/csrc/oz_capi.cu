@@ -159,6 +159,23 @@ static int read_leaf_count(oz_engine* e, int* n) {
     return OZ_OK;
 }
 
+__global__ void count_waiting_kernel(const OzTreeParams P, int* out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < P.G && P.status[g] == OZ_GAME_WAIT_LEAF) atomicAdd(out, 1);
+}
+
+static int count_waiting(oz_engine* e, int* n) {
+    int* d = e->tp.leaf_count + 2;
+    OZ_CUDA(cudaMemsetAsync(d, 0, sizeof(int), e->stream));
+    count_waiting_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, d);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
+    OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[4], d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaStreamSynchronize(e->stream));
+    *n = e->h_pinned[4];
+    return OZ_OK;
+}
+
 // Evaluate the pending leaf batch with the device network (count stays on the device).
 static int eval_leaves_net(oz_engine* e) {
     int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, e->leaf_logits,
@@ -167,19 +184,32 @@ static int eval_leaves_net(oz_engine* e) {
     return oz_tree_cache_publish(e);
 }
 
+// Evaluate the parked leaves with whatever this engine's prior source is (device network / closed-form hash).
+static int eval_leaves(oz_engine* e) {
+    if (e->cfg.prior_mode == OZ_PRIOR_NET) return eval_leaves_net(e);
+    return oz_tree_hash_eval(e);
+}
+
 static int search_pump(oz_engine* e, int32_t* n_leaves) {
     OzTreeParams& P = e->tp;
     const int mode = e->cfg.prior_mode;
+    const bool inline_hash = mode == OZ_PRIOR_HASH && P.vl_width <= 1;  // whole search inside one launch
     while (true) {
         OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
         int rc = oz_tree_step(e);
         if (rc) return rc;
-        if (mode == OZ_PRIOR_HASH) { *n_leaves = 0; break; }
+        if (inline_hash) { *n_leaves = 0; break; }
+        // finished when no game is parked any more (a wave made only of cache hits parks games without emitting leaves)
         int nl = 0;
         if ((rc = read_leaf_count(e, &nl))) return rc;
-        if (nl == 0) { *n_leaves = 0; break; }
-        if (mode == OZ_PRIOR_HOST) { e->host_leaves = nl; *n_leaves = nl; return OZ_OK; }
-        if ((rc = eval_leaves_net(e))) return rc;
+        if (mode == OZ_PRIOR_HOST) {
+            if (nl == 0) { *n_leaves = 0; break; }
+            e->host_leaves = nl; *n_leaves = nl; return OZ_OK;
+        }
+        int waiting = 0;
+        if ((rc = count_waiting(e, &waiting))) return rc;
+        if (waiting == 0) { *n_leaves = 0; break; }
+        if (nl > 0 && (rc = eval_leaves(e))) return rc;
     }
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     e->host_leaves = 0;
@@ -314,7 +344,7 @@ extern "C" int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active) {
     if (!e->search_started || !e->tp.selfplay) { oz_set_error("oz_selfplay_begin first"); return OZ_ERR_STATE; }
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     OzTreeParams& P = e->tp;
-    const bool net = e->cfg.prior_mode == OZ_PRIOR_NET;
+    const bool need_eval = e->cfg.prior_mode == OZ_PRIOR_NET || P.vl_width > 1;
     int active = -1;
     long long done = 0;
     u64 last_sims = ~0ull;
@@ -326,7 +356,7 @@ extern "C" int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active) {
             OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
             int rc = oz_tree_step(e);
             if (rc) return rc;
-            if (net && (rc = eval_leaves_net(e))) return rc;
+            if (need_eval && (rc = eval_leaves(e))) return rc;
         }
         done += chunk;
         OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[2], P.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));

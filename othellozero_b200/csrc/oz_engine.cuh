@@ -118,6 +118,7 @@ int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white,
 int oz_tree_step(oz_engine* e);  // one tree kernel launch
 int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev);
 int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev);
+int oz_tree_hash_eval(oz_engine* e);      // wave mode + closed-form priors: evaluate the parked leaves
 int oz_tree_cache_publish(oz_engine* e);  // after a leaf batch has been evaluated
 int oz_tree_cache_clear(oz_engine* e);    // weights changed
 

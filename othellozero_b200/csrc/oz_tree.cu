@@ -378,13 +378,15 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
             // priors for this lane's two squares, row layout r*n+c with row stride 64
             float pi_lo = 0.f, pi_hi = 0.f;
+            // li >= 0: row of the evaluated leaf batch; li <= -2: evaluation-cache entry -(li+2) (wave mode parks hits too)
+            const float* prow = (li >= 0) ? P.leaf_pi + (size_t)li * 64 : P.cache_pi + (size_t)(-(li + 2)) * 64;
             {
                 int r = lane >> 3, c = lane & 7;
-                if (r < n && c < n) pi_lo = P.leaf_pi[(size_t)li * 64 + r * n + c];
+                if (r < n && c < n) pi_lo = prow[r * n + c];
                 r += 4;
-                if (r < n && c < n) pi_hi = P.leaf_pi[(size_t)li * 64 + r * n + c];
+                if (r < n && c < n) pi_hi = prow[r * n + c];
             }
-            const float v = P.leaf_v[li];
+            const float v = (li >= 0) ? P.leaf_v[li] : P.cache_v[-(li + 2)];
             bool created;
             if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
                 if (lane == 0) P.status[slot] = OZ_GAME_POOL_FULL;
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             continue;
         }
         // leaf
-        if (P.prior_mode == OZ_PRIOR_HASH) {
+        if (P.prior_mode == OZ_PRIOR_HASH && !vl) {
             u64 key = sm64(pd.own ^ sm64(pd.opp));
             float pi_lo = hash_pi(key, lane), pi_hi = hash_pi(key, lane + 32);
             float v = hash_v(key);
@@ -580,7 +582,11 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         u64 cfp = 0;
         if (P.cache_tags) {
             cres = cache_probe(P, pd.own, pd.opp, lane, &cfp, &cidx, &li);
-            if (cres == CACHE_HIT) {
+            if (cres == CACHE_HIT && vl) {
+                // wave mode: keep the wave's composition independent of the cache - park the hit like any other leaf
+                ++c_hits;
+                li = -(cidx + 2);
+            } else if (cres == CACHE_HIT) {
                 const int r = lane >> 3, c = lane & 7;
                 float pi_lo = 0.f, pi_hi = 0.f;
                 const float* row = P.cache_pi + (size_t)cidx * 64;
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         }
         if (cres == CACHE_ALIAS) {
             ++c_alias;
-        } else {
+        } else if (li > -2) {
             if (lane == 0) li = atomicAdd(P.leaf_count, 1);
             li = __shfl_sync(FULLW, li, 0);
             if (lane == 0) {
@@ -648,6 +654,21 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         if (c_moves) atomicAdd(&P.counters[7], c_moves);
         atomicMax(&P.counters[5], (u64)c_depth);
     }
+}
+
+// Wave mode with the closed-form priors: the "network" is this kernel, so that waves are formed exactly as with a
+// real evaluator (leaves parked, evaluated together, expanded at the next step).
+__global__ void hash_eval_kernel(const OzTreeParams P, float* __restrict__ pi, float* __restrict__ v) {
+    const int lane = threadIdx.x & 31;
+    const int li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (li >= *P.leaf_count) return;
+    const u64 key = sm64(P.leaf_own[li] ^ sm64(P.leaf_opp[li]));
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int sq = lane + 32 * half, r = sq >> 3, c = sq & 7;
+        if (r < P.n && c < P.n) pi[(size_t)li * 64 + r * P.n + c] = hash_pi(key, sq);
+    }
+    if (lane == 0) v[li] = hash_v(key);
 }
 
 // MCTS.N(root, action) for every game (MCTS/__init__.py:73-84).
@@ -892,5 +913,13 @@ int oz_tree_cache_clear(oz_engine* e) {
     OzTreeParams& P = e->tp;
     if (!P.cache_tags) return OZ_OK;
     OZ_CUDA(cudaMemsetAsync(P.cache_tags, 0, e->cache_entries * sizeof(u64), e->stream));
+    return OZ_OK;
+}
+
+int oz_tree_hash_eval(oz_engine* e) {
+    OzTreeParams& P = e->tp;
+    hash_eval_kernel<<<(P.G * P.vl_width + 7) / 8, 256, 0, e->stream>>>(P, e->leaf_pi, e->leaf_v);
+    OZ_CUDA(cudaGetLastError());
+    e->launches++;
     return OZ_OK;
 }
