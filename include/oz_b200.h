@@ -91,6 +91,13 @@ int oz_rules_apply_dev(int32_t board_size, const uint64_t* own, const uint64_t* 
                        uint64_t* own_out, uint64_t* opp_out, uint32_t* flags, uint64_t* next_legal, int64_t n,
                        void* stream);
 
+/* get_board_players_points (:258-260): disc counts per colour; the winner is BLACK iff black_points >= white_points
+ * (max() over the dict in BLACK, WHITE order, :254-256). */
+int oz_rules_score_host(int32_t device, const uint64_t* black, const uint64_t* white, int32_t* black_points,
+                        int32_t* white_points, int64_t n);
+int oz_rules_score_dev(const uint64_t* black, const uint64_t* white, int32_t* black_points, int32_t* white_points,
+                       int64_t n, void* stream);
+
 /* ---- perft / random playouts: RandomOthelloAgent loop, agents.py:20-24,71-84 ------------- */
 /* Game g (global id first_game_id+g) starts at initial_board(board_size) and plays
  * legal[mulhi32(sm64(sm64(seed ^ id) + p) >> 32, popcount(legal))] at move index p (ascending bit order ==

@@ -36,6 +36,8 @@ SIGNATURES = {
     "oz_rules_legal_moves_dev": (C.c_int, [C.c_int32, vp, vp, vp, C.c_int64, vp]),
     "oz_rules_apply_host": (C.c_int, [C.c_int32, C.c_int32, u64p, u64p, i32p, u64p, u64p, u32p, u64p, C.c_int64]),
     "oz_rules_apply_dev": (C.c_int, [C.c_int32, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]),
+    "oz_rules_score_host": (C.c_int, [C.c_int32, u64p, u64p, i32p, i32p, C.c_int64]),
+    "oz_rules_score_dev": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     "oz_perft_playouts_host": (C.c_int, [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, u64p,
                                          u64p, u32p, u8p]),
     "oz_perft_playouts_dev": (C.c_int, [C.c_int32, C.c_uint64, C.c_uint64, C.c_int64, C.c_int32, vp, vp, vp, vp, vp]),

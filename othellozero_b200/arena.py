@@ -139,6 +139,5 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
     finally:
         for e in engines:
             e.close()
-    cb = np.array([bin(int(x)).count("1") for x in black])
-    cw = np.array([bin(int(x)).count("1") for x in white])
+    cb, cw = _e.score(black, white, device)
     return dict(winner=np.where(cb >= cw, 0, 1), black=black, white=white, plies=plies, points=np.maximum(cb, cw))

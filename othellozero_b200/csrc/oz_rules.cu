@@ -41,6 +41,16 @@ rules_apply_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, con
     }
 }
 
+// get_board_players_points (Othello/__init__.py:258-260): popcount scoring.
+__global__ void __launch_bounds__(256) rules_score_kernel(const u64* __restrict__ a, const u64* __restrict__ b,
+                                                          int* __restrict__ ca, int* __restrict__ cb, long long n) {
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        ca[i] = popc(a[i]);
+        cb[i] = popc(b[i]);
+    }
+}
+
 // One thread = one whole random game; nothing but the final position touches memory.
 __global__ void __launch_bounds__(256)
 perft_playout_kernel(int n, u64 full, u64 seed, u64 first_id, long long n_games, int max_moves,
@@ -114,6 +124,15 @@ extern "C" int oz_rules_apply_dev(int32_t board_size, const uint64_t* own, const
     return OZ_OK;
 }
 
+extern "C" int oz_rules_score_dev(const uint64_t* black, const uint64_t* white, int32_t* black_points,
+                                  int32_t* white_points, int64_t n, void* stream) {
+    if (n <= 0) return OZ_OK;
+    rules_score_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const u64*)black, (const u64*)white,
+                                                                           black_points, white_points, n);
+    OZ_CUDA(cudaGetLastError());
+    return OZ_OK;
+}
+
 extern "C" int oz_perft_playouts_dev(int32_t board_size, uint64_t seed, uint64_t first_game_id, int64_t n_games,
                                      int32_t max_moves, uint64_t* black, uint64_t* white, uint32_t* info,
                                      uint8_t* moves, void* stream) {
@@ -181,6 +200,23 @@ extern "C" int oz_rules_apply_host(int32_t device, int32_t board_size, const uin
     OZ_CUDA(cudaMemcpy(opp_out, ob.p, b8, cudaMemcpyDeviceToHost));
     OZ_CUDA(cudaMemcpy(flags, f.p, b4, cudaMemcpyDeviceToHost));
     if (next_legal) OZ_CUDA(cudaMemcpy(next_legal, nl.p, b8, cudaMemcpyDeviceToHost));
+    return OZ_OK;
+}
+
+extern "C" int oz_rules_score_host(int32_t device, const uint64_t* black, const uint64_t* white, int32_t* black_points,
+                                   int32_t* white_points, int64_t n) {
+    OZ_REQUIRE(n >= 0 && (n == 0 || (black && white && black_points && white_points)), "null buffer");
+    if (n == 0) return OZ_OK;
+    OZ_CUDA(cudaSetDevice(device));
+    DevBuf a, b, ca, cb;
+    size_t b8 = (size_t)n * 8, b4 = (size_t)n * 4;
+    if (a.alloc(b8) || b.alloc(b8) || ca.alloc(b4) || cb.alloc(b4)) return OZ_ERR_NOMEM;
+    OZ_CUDA(cudaMemcpy(a.p, black, b8, cudaMemcpyHostToDevice));
+    OZ_CUDA(cudaMemcpy(b.p, white, b8, cudaMemcpyHostToDevice));
+    int rc = oz_rules_score_dev((const uint64_t*)a.p, (const uint64_t*)b.p, (int32_t*)ca.p, (int32_t*)cb.p, n, nullptr);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpy(black_points, ca.p, b4, cudaMemcpyDeviceToHost));
+    OZ_CUDA(cudaMemcpy(white_points, cb.p, b4, cudaMemcpyDeviceToHost));
     return OZ_OK;
 }
 

@@ -44,6 +44,16 @@ def apply_moves(own, opp, sq, board_size: int = 8, device: int = 0):
     return o2, p2, fl, nl
 
 
+def score(black, white, device: int = 0):
+    """get_board_players_points (Othello/__init__.py:258-260) -> (black_points, white_points) int32 arrays."""
+    black, white = _u64(np.atleast_1d(black)), _u64(np.atleast_1d(white))
+    cb = np.zeros(black.shape, dtype=np.int32)
+    cw = np.zeros(black.shape, dtype=np.int32)
+    check(_lib.load().oz_rules_score_host(device, ptr(black, u64p), ptr(white, u64p), ptr(cb, i32p), ptr(cw, i32p),
+                                          black.size))
+    return cb, cw
+
+
 def perft_playouts(n_games: int, board_size: int = 8, seed: int = 0, first_game_id: int = 0, max_moves: int = -1,
                    want_moves: bool = False, device: int = 0):
     """Random playouts (agents.py:20-24,71-84) with the engine RNG.  Returns dict of arrays."""

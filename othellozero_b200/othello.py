@@ -239,7 +239,9 @@ class OthelloGame:
 
     @staticmethod
     def get_board_players_points(board):
-        return {p: np.count_nonzero(board[:, :, OthelloGame.PLAYER_CHANNELS[p]]) for p in OthelloPlayer}
+        black, white = _bits(board)
+        cb, cw = _e.score([black], [white], OthelloGame.device)
+        return {OthelloPlayer.BLACK: int(cb[0]), OthelloPlayer.WHITE: int(cw[0])}
 
     @staticmethod
     def has_player_actions_on_board(board, player):
