@@ -460,12 +460,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-moves", type=int, default=1)
     ap.add_argument("--eval-cache-log2", type=int, default=24)
+    ap.add_argument("--conv2", default="table", choices=["table", "gemm"],
+                    help="conv2 as the conv1∘conv2 partial-product table gather (default) or as the tcgen05 implicit GEMM")
     ap.add_argument("--vl", type=int, default=1, help="virtual-loss wave width (configs[3]); 1 = sequential, bit-exact")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         return run_reference(args)
+    os.environ["OZ_NET_CONV2"] = args.conv2  # read by the engine when it is created
     return run_ours(args)
 
 

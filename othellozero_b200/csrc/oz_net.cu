@@ -32,6 +32,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int GEMM_THREADS = 256;
 constexpr int EPI_RELU_BF16 = 0;
 constexpr int EPI_HEADS = 1;
+constexpr int EPI_LINEAR_BF16 = 2;  // no bias, no ReLU: builds the conv2 partial-product table
 constexpr int N_PATTERNS = 19683;  // 3^9
 
 struct GemmParams {
@@ -294,7 +295,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const long long grow = (long long)m_tile * p.rows_valid + r;
             const bool ok = (r < p.rows_valid) && (grow < (long long)L * p.rows_per_board);
             const uint32_t t_row = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
-            if constexpr (EPI == EPI_RELU_BF16) {
+            if constexpr (EPI == EPI_RELU_BF16 || EPI == EPI_LINEAR_BF16) {
+                constexpr float LO = (EPI == EPI_RELU_BF16) ? 0.0f : -3.0e38f;
                 bf16* orow = p.out + grow * p.ldc + (long long)n_idx * BLOCK_N;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -305,8 +307,8 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         uint32_t packed[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], 0.0f);
-                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.0f);
+                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], LO);
+                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], LO);
                             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
                             packed[j] = *reinterpret_cast<uint32_t*>(&h);
                         }
@@ -646,6 +648,111 @@ conv1_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, co
     }
 }
 
+// ---- conv1∘conv2 as a table gather ------------------------------------------------------------------------
+// conv2's input at square q is table1[pat(q)], one of 3^9 vectors, so tap t's contribution W2'[t] · act1[q] to the
+// output at q - offset(t) is one of 19683 x 9 pre-computable vectors:
+//     table2[pat][t][co] = bf16( sum_ci W2'[co][t*C+ci] * table1[pat][ci] )      (fp32 accumulate, built at weight load
+//                                                                                  by the tcgen05 GEMM below)
+//     act2[b][y][x][co]  = bf16( relu( bias2'[co] + sum_{t : (y+ky-1, x+kx-1) on the board} table2[pat(y+ky-1,x+kx-1)][t][co] ) )
+// i.e. 302 MFLOP per 8x8 board become <= 576 (484 on-board) 1-KB row reads + fp32 adds: the layer moves from the
+// tensor roofline to the HBM/L2 roofline (484 KB read + 64 KB written per board at C=512) and conv1's output is never
+// materialised.  Squares outside the board are conv2's zero padding (NOT pattern 0): they read the all-zero row
+// N_PATTERNS, which stays in L1.
+__global__ void permute_conv2_weights_kernel(const bf16* __restrict__ w /*[co][t*C+ci]*/, int C, bf16* __restrict__ wr /*[t*C+co][ci]*/) {
+    const size_t total = 9ull * C * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % C);
+        const size_t r = i / C;
+        const int co = (int)(r % C), t = (int)(r / C);
+        wr[i] = w[(size_t)co * 9 * C + (size_t)t * C + ci];
+    }
+}
+
+template <int NJ>  // 16-byte chunks per lane: C = 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
+__global__ void __launch_bounds__(256, 2)
+conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count,
+                          int max_count, int n, int C, const bf16* __restrict__ table2, const float* __restrict__ bias,
+                          bf16* __restrict__ out) {
+    __shared__ int s_pat[100];  // (n+2) x (n+2) patterns with a border of N_PATTERNS (the zero row)
+    int L = *count;
+    if (L > max_count) L = max_count;
+    const int nsq = n * n, np2 = n + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cpr = C >> 3;  // 16-byte chunks per row
+    float bs[NJ][8];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int ch = lane + 32 * j;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bs[j][i] = ch < cpr ? bias[ch * 8 + i] : 0.f;
+    }
+    const uint4* tab = reinterpret_cast<const uint4*>(table2);
+    for (int b = blockIdx.x; b < L; b += gridDim.x) {
+        const u64 o = own[b], q = opp[b];
+        if (threadIdx.x < np2 * np2) {
+            const int py = threadIdx.x / np2, px = threadIdx.x - py * np2;
+            const int y = py - 1, x = px - 1;
+            int pat = N_PATTERNS;
+            if (y >= 0 && y < n && x >= 0 && x < n) {
+                pat = 0;
+                int mul = 1;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                    int s = 0;
+                    if (yy >= 0 && yy < n && xx >= 0 && xx < n) {
+                        const int bit = yy * 8 + xx;
+                        s = (int)((o >> bit) & 1ull) + 2 * (int)((q >> bit) & 1ull);
+                    }
+                    pat += s * mul;
+                    mul *= 3;
+                }
+            }
+            s_pat[threadIdx.x] = pat;
+        }
+        __syncthreads();
+        for (int pos = warp; pos < nsq; pos += 8) {
+            const int y = pos / n, x = pos - y * n;
+            uint4 v[9][NJ];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int pat = s_pat[(y + t / 3) * np2 + (x + t % 3)];  // padded coordinates of (y+ky-1, x+kx-1)
+                const uint4* row = tab + ((size_t)pat * 9 + t) * cpr;
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int ch = lane + 32 * j;
+                    v[t][j] = ch < cpr ? __ldg(row + ch) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            bf16* orow = out + ((size_t)b * nsq + pos) * C;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = bs[j][i];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const uint32_t w4[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[2 * i] += __uint_as_float(w4[i] << 16);
+                        acc[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
+                    }
+                }
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
+                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                const int ch = lane + 32 * j;
+                if (ch < cpr) reinterpret_cast<uint4*>(orow)[ch] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- weight folding -------------------------------------------------------------------------------------
 // Keras kernel W[k][o] (HWIO flattened / Dense (in,out)) -> Wt[o][k] bf16 with the BN scale folded;
 // bias'[o] = (b - mean) * s + beta.
@@ -713,6 +820,10 @@ struct OzNet {
     long forwards = 0;
     int sm_count = 148;
     bf16* table1 = nullptr;
+    // conv1∘conv2 partial-product table [19683 + 1 zero row][9 taps][C] (OZ_NET_CONV2=gemm keeps the implicit GEMM instead)
+    bool conv2_table = true;
+    bf16* table2 = nullptr; bf16* w2perm = nullptr; float* zero_bias = nullptr; int* d_npat = nullptr;
+    OzLayer tbl;
     bf16 *w[6] = {nullptr}; float* bias[6] = {nullptr};  // conv2, conv3, conv4, fc1, fc2, heads
     bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *act4 = nullptr, *f1 = nullptr, *f2 = nullptr;
     OzLayer layer[6];
@@ -767,6 +878,8 @@ int oz_net_create(oz_engine* e) {
     net->timing = t && t[0] == '1';
     const char* pd = getenv("OZ_NET_NO_PDL");
     net->pdl = !(pd && pd[0] == '1');
+    const char* c2 = getenv("OZ_NET_CONV2");
+    net->conv2_table = !(c2 && c2[0] == 'g');
     const char* te = getenv("OZ_NET_TIMING_EVERY");
     if (te && atoi(te) > 0) net->timing_every = atoi(te);
     int dev = e->cfg.device;
@@ -814,12 +927,12 @@ static int make_map_B(CUtensorMap* m, bf16* base, int K, int Nout, int block_n) 
 }
 
 // layer li: input [B][ih][iw][cin] -> output [B][oh*ow][nout]; ntaps 3 (conv) or 1 (fc)
-static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, int ow, int oh, int ntaps, int pad, int nout_pad,
-                       int block_n, int epi, bf16* out, int ldc) {
-    OzLayer& Lr = net->layer[li];
+static int setup_layer(OzNet* net, OzLayer& Lr, bf16* weights, const float* bias, int bmax, bf16* in, int cin, int iw, int ih,
+                       int ow, int oh, int ntaps, int pad, int nout_pad, int block_n, int epi, bf16* out, int ldc) {
     GemmParams& p = Lr.p;
     memset(&p, 0, sizeof(p));
     if (epi == EPI_RELU_BF16) block_n = (nout_pad % 256 == 0) ? 256 : 128;
+    if (epi == EPI_LINEAR_BF16) block_n = (nout_pad % 256 == 0) ? 256 : 128;
     const int rows_per_board = ow * oh;
     int nb = BLOCK_M / rows_per_board;
     if (nb > 256) nb = 256;
@@ -844,27 +957,27 @@ static int setup_layer(OzNet* net, int li, bf16* in, int cin, int iw, int ih, in
     p.num_kb = ntaps * ntaps * p.chunks_per_tap;
     p.n_tiles = nout_pad / block_n;
     p.ldc = ldc;
-    p.max_count = net->Bmax;
+    p.max_count = bmax;
     p.a_bytes = (unsigned)(p.rows_valid * BLOCK_K * 2);
-    p.bias = net->bias[li];
+    p.bias = bias;
     p.out = out;
     p.nsq = net->n * net->n;
     Lr.block_n = block_n;
     Lr.epi = epi;
-    Lr.max_tiles = ((net->Bmax * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
-    int rc = make_map_A(&Lr.mapA, in, cin, iw, ih, net->Bmax, ow, oh, nb);
+    Lr.max_tiles = ((bmax * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
+    int rc = make_map_A(&Lr.mapA, in, cin, iw, ih, bmax, ow, oh, nb);
     if (rc) return rc;
-    rc = make_map_A(&Lr.mapA2, in, cin, iw, ih, net->Bmax, ow, p.split ? oh / 2 : oh, p.split ? 1 : nb);
+    rc = make_map_A(&Lr.mapA2, in, cin, iw, ih, bmax, ow, p.split ? oh / 2 : oh, p.split ? 1 : nb);
     if (rc) return rc;
     static const bool allow_2sm = !(getenv("OZ_NET_NO_2SM") && getenv("OZ_NET_NO_2SM")[0] == '1');
     // measured (B200, 4096 boards): the SM-pair kernel wins on conv2 (0.938 vs 0.955 ms), ties on conv4/fc1/fc2 and loses
     // on the split-tile conv3 (0.620 vs 0.596 ms) - the step is power-capped, not L2- or SMEM-bound
     Lr.use_2sm = allow_2sm && epi == EPI_RELU_BF16 && block_n == 256 && !p.split;
     if (Lr.use_2sm) {
-        rc = make_map_B(&Lr.mapB2, net->w[li], ntaps * ntaps * cin, nout_pad, 128);
+        rc = make_map_B(&Lr.mapB2, weights, ntaps * ntaps * cin, nout_pad, 128);
         if (rc) return rc;
     }
-    return make_map_B(&Lr.mapB, net->w[li], ntaps * ntaps * cin, nout_pad, block_n);
+    return make_map_B(&Lr.mapB, weights, ntaps * ntaps * cin, nout_pad, block_n);
 }
 
 int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels, bool on_device) {
@@ -891,13 +1004,33 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         NA(net->act1, (size_t)B * nsq * C * 2) NA(net->act2, (size_t)B * nsq * C * 2)
         NA(net->act3, (size_t)B * o2 * o2 * C * 2) NA(net->act4, (size_t)B * o4 * o4 * C * 2)
         NA(net->f1, (size_t)B * 1024 * 2) NA(net->f2, (size_t)B * 512 * 2)
+        if (net->conv2_table) {
+            NA(net->table2, (size_t)(N_PATTERNS + 1) * 9 * C * 2) NA(net->w2perm, kc * 2)
+            NA(net->zero_bias, 9ull * C * 4) NA(net->d_npat, 16)
+        }
 #undef NA
-        if ((rc = setup_layer(net, 0, net->act1, C, n, n, n, n, 3, 1, C, 256, EPI_RELU_BF16, net->act2, C))) return rc;
-        if ((rc = setup_layer(net, 1, net->act2, C, n, n, o2, o2, 3, 0, C, 256, EPI_RELU_BF16, net->act3, C))) return rc;
-        if ((rc = setup_layer(net, 2, net->act3, C, o2, o2, o4, o4, 3, 0, C, 256, EPI_RELU_BF16, net->act4, C))) return rc;
-        if ((rc = setup_layer(net, 3, net->act4, K1, 1, 1, 1, 1, 1, 0, 1024, 256, EPI_RELU_BF16, net->f1, 1024))) return rc;
-        if ((rc = setup_layer(net, 4, net->f1, 1024, 1, 1, 1, 1, 1, 0, 512, 256, EPI_RELU_BF16, net->f2, 512))) return rc;
-        if ((rc = setup_layer(net, 5, net->f2, 512, 1, 1, 1, 1, 1, 0, 128, 128, EPI_HEADS, nullptr, 64))) return rc;
+#define SL(li, ...) if ((rc = setup_layer(net, net->layer[li], net->w[li], net->bias[li], B, __VA_ARGS__))) return rc;
+        SL(0, net->act1, C, n, n, n, n, 3, 1, C, 256, EPI_RELU_BF16, net->act2, C)
+        SL(1, net->act2, C, n, n, o2, o2, 3, 0, C, 256, EPI_RELU_BF16, net->act3, C)
+        SL(2, net->act3, C, o2, o2, o4, o4, 3, 0, C, 256, EPI_RELU_BF16, net->act4, C)
+        SL(3, net->act4, K1, 1, 1, 1, 1, 1, 0, 1024, 256, EPI_RELU_BF16, net->f1, 1024)
+        SL(4, net->f1, 1024, 1, 1, 1, 1, 1, 0, 512, 256, EPI_RELU_BF16, net->f2, 512)
+        SL(5, net->f2, 512, 1, 1, 1, 1, 1, 0, 128, 128, EPI_HEADS, nullptr, 64)
+#undef SL
+        if (net->conv2_table) {
+            // table2 = table1 [19683 x C] x W2perm^T [C x 9C]: one "fc" launch of the GEMM kernel with a linear epilogue
+            if ((rc = setup_layer(net, net->tbl, net->w2perm, net->zero_bias, N_PATTERNS, net->table1, C, 1, 1, 1, 1, 1, 0,
+                                  9 * C, 256, EPI_LINEAR_BF16, net->table2, 9 * C))) return rc;
+            OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<256, EPI_LINEAR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmSmem<256>::DYN_BYTES));
+            OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_LINEAR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmSmem<128>::DYN_BYTES));
+            OZ_CUDA(cudaMemsetAsync(net->table2 + (size_t)N_PATTERNS * 9 * C, 0, 9ull * C * 2, st));  // the padding row
+            OZ_CUDA(cudaMemsetAsync(net->zero_bias, 0, 9ull * C * 4, st));
+            const int npat = N_PATTERNS;
+            OZ_CUDA(cudaMemcpyAsync(net->d_npat, &npat, sizeof(int), cudaMemcpyHostToDevice, st));
+            OZ_CUDA(cudaStreamSynchronize(st));
+        }
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<256, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmSmem<256>::DYN_BYTES));
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_HEADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -934,6 +1067,25 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         fold_weights_kernel<<<dim3((K + 31) / 32, (C + 31) / 32), tb, 0, st>>>(w, b, g, be, mu, va, eps, K, C, net->w[li], net->bias[li]);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
+    }
+    if (net->conv2_table) {  // table2[pat][t][:] = W2'[t] . table1[pat]  (93 GFLOP at C=512, once per weight load)
+        permute_conv2_weights_kernel<<<net->sm_count * 8, 256, 0, st>>>(net->w[0], C, net->w2perm);
+        OZ_CUDA(cudaGetLastError());
+        OzLayer& Lr = net->tbl;
+        GemmParams p = Lr.p;
+        p.count = net->d_npat;
+        cudaLaunchConfig_t cfg{};
+        cfg.blockDim = dim3(GEMM_THREADS);
+        cfg.gridDim = dim3(Lr.max_tiles < net->sm_count ? Lr.max_tiles : net->sm_count);
+        cfg.stream = st;
+        if (Lr.block_n == 256) {
+            cfg.dynamicSmemBytes = GemmSmem<256>::DYN_BYTES;
+            OZ_CUDA(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<256, EPI_LINEAR_BF16>, Lr.mapA, Lr.mapA2, Lr.mapB, p));
+        } else {
+            cfg.dynamicSmemBytes = GemmSmem<128>::DYN_BYTES;
+            OZ_CUDA(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<128, EPI_LINEAR_BF16>, Lr.mapA, Lr.mapA2, Lr.mapB, p));
+        }
+        e->launches += 2;
     }
     {   // fc1 + bn5
         const float* w = take((int64_t)K1 * 1024); const float* b = take(1024);
@@ -981,15 +1133,28 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         net->ev_next = (net->ev_next + 1) % OzNet::RING;
         cudaEventRecord(ev[0], st);
     }
-    {
-        (void)nsq;
+    (void)nsq;
+    if (!net->conv2_table) {
         int blocks = max_count < net->sm_count * 8 ? max_count : net->sm_count * 8;  // 8 resident CTAs/SM, grid-stride
         conv1_gather_kernel<<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, net->table1, net->act1);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
     }
     if (tm) cudaEventRecord(ev[1], st);
-    for (int li = 0; li < 6; ++li) {
+    if (net->conv2_table) {  // conv1 + conv2 in one gather-sum over the partial-product table
+        int blocks = max_count < net->sm_count * 2 ? max_count : net->sm_count * 2;  // 2 resident CTAs/SM, grid-stride
+        const bf16* t2 = net->table2; const float* b2 = net->bias[0];
+        switch (C / 256) {
+            case 0: case 1: conv2_table_gather_kernel<1><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
+            case 2: conv2_table_gather_kernel<2><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
+            case 3: conv2_table_gather_kernel<3><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
+            default: conv2_table_gather_kernel<4><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
+        }
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+        if (tm) cudaEventRecord(ev[2], st);
+    }
+    for (int li = net->conv2_table ? 1 : 0; li < 6; ++li) {
         OzLayer& Lr = net->layer[li];
         GemmParams p = Lr.p;
         p.count = count_dev;
@@ -1063,6 +1228,10 @@ int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes) {
     int64_t sizes[6] = {(int64_t)B * n * n * C, (int64_t)B * n * n * C, (int64_t)B * (n - 2) * (n - 2) * C,
                         (int64_t)B * (n - 4) * (n - 4) * C, (int64_t)B * 1024, (int64_t)B * 512};
     OZ_REQUIRE(layer >= 0 && layer < 6, "layer %d out of range", layer);
+    if (layer == 0 && net->conv2_table) {
+        oz_set_error("conv1's output is not materialised while conv2 runs as the table gather (OZ_NET_CONV2=gemm keeps it)");
+        return OZ_ERR_STATE;
+    }
     OZ_REQUIRE(bytes >= 0 && bytes <= sizes[layer] * 2, "bytes out of range");
     OZ_CUDA(cudaMemcpyAsync(host, ptrs[layer], (size_t)bytes, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaStreamSynchronize(e->stream));

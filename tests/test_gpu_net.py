@@ -22,7 +22,15 @@ def _positions(n, count, seed):
     return np.array(own, dtype=np.uint64), np.array(opp, dtype=np.uint64)
 
 
-def _check(n, C, B, max_games, seed, randomize_bn=True):
+@pytest.fixture(params=["table", "gemm"])
+def conv2_mode(request, monkeypatch):
+    """conv2 runs either as the conv1∘conv2 partial-product table gather (default) or as the tcgen05 implicit GEMM;
+    the mode is read from OZ_NET_CONV2 when an engine is created."""
+    monkeypatch.setenv("OZ_NET_CONV2", request.param)
+    return request.param
+
+
+def _check(n, C, B, max_games, seed, randomize_bn=True, conv2_mode="table"):
     import torch
     from othellozero_b200 import engine, net
     blob = net.init_weights(n, C, seed=seed, randomize_bn=randomize_bn)
@@ -37,7 +45,10 @@ def _check(n, C, B, max_games, seed, randomize_bn=True):
     # layer-by-layer first: localises a failure
     rows = [n * n, n * n, (n - 2) ** 2, (n - 4) ** 2, 1, 1]
     chans = [C, C, C, C, 1024, 512]
-    for li in range(6):
+    if conv2_mode == "table":
+        with pytest.raises(RuntimeError):
+            e.activation(0, B, rows[0], chans[0])   # conv1's output is never materialised in this mode
+    for li in range(1 if conv2_mode == "table" else 0, 6):
         got = e.activation(li, B, rows[li], chans[li])
         ref = hidden[li]
         scale = max(1.0, float(np.abs(ref).max()))
@@ -51,24 +62,49 @@ def _check(n, C, B, max_games, seed, randomize_bn=True):
     return lg, v
 
 
-def test_net_8x8_c512_ragged_batch():
+def test_net_8x8_c512_ragged_batch(conv2_mode):
     # 301 boards: not a multiple of any tile's boards-per-tile (2, 3, 8, 128)
-    _check(8, 512, 301, 512, seed=1)
+    _check(8, 512, 301, 512, seed=1, conv2_mode=conv2_mode)
 
 
-def test_net_8x8_keras_default_init():
-    _check(8, 512, 64, 64, seed=2, randomize_bn=False)
+def test_net_8x8_keras_default_init(conv2_mode):
+    _check(8, 512, 64, 64, seed=2, randomize_bn=False, conv2_mode=conv2_mode)
 
 
-def test_net_6x6_c512():
-    _check(6, 512, 130, 256, seed=3)
+def test_net_6x6_c512(conv2_mode):
+    _check(6, 512, 130, 256, seed=3, conv2_mode=conv2_mode)
 
 
-def test_net_small_channels_single_board():
-    _check(8, 128, 1, 8, seed=4)
+def test_net_small_channels_single_board(conv2_mode):
+    _check(8, 128, 1, 8, seed=4, conv2_mode=conv2_mode)
 
 
-def test_net_is_row_independent():
+@pytest.mark.parametrize("C", [256, 768, 1024])
+def test_net_other_channel_counts(C, conv2_mode):
+    _check(8, C, 37, 64, seed=12, conv2_mode=conv2_mode)
+
+
+def test_conv2_table_vs_gemm_agree(monkeypatch):
+    """The two conv2 formulations differ only in where the nine tap sums are rounded to bf16."""
+    from othellozero_b200 import engine, net
+    n, C = 8, 512
+    blob = net.init_weights(n, C, seed=21, randomize_bn=True)
+    own, opp = _positions(n, 150, 21)
+    outs = []
+    for mode in ("table", "gemm"):
+        monkeypatch.setenv("OZ_NET_CONV2", mode)
+        e = engine.Engine(n, max_games=256, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+        e.load_weights(blob, C)
+        pi, lg, v = e.net_forward(own, opp)
+        a2 = e.activation(1, 150, 64, C)
+        outs.append((lg, v, a2))
+        e.close()
+    scale = max(1.0, float(np.abs(outs[1][2]).max()))
+    assert np.abs(outs[0][2] - outs[1][2]).max() <= 0.02 * scale
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= TOL and np.abs(outs[0][1] - outs[1][1]).max() <= TOL
+
+
+def test_net_is_row_independent(conv2_mode):
     """A board's output must not depend on its position in the batch or on its neighbours."""
     from othellozero_b200 import engine, net
     n, C = 8, 128
