@@ -54,6 +54,7 @@ struct GemmParams {
     int n_tiles;         // Nout / BLOCK_N
     int ldc;             // output row stride in elements
     int max_count;
+    unsigned long long* trace;  // {min start ns, max end ns} of this launch, or null
     unsigned a_bytes;    // TMA bytes per A stage
     const int* count;    // device: number of boards in this batch
     const float* bias;   // [Nout] fp32 (BN folded)
@@ -163,6 +164,35 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Table entries are consumed by fp32 accumulation only, so the pair (even, odd) is packed so that the odd element needs no
+// extraction: the low half holds bf16_rn(even) as usual, and the high half is chosen such that the WHOLE 32-bit word, read
+// as an fp32, is the representable value closest to `odd` (the low half then acts as 16 extra mantissa bits).  Candidates
+// are 2^16 fp32-ulps apart, so |word - odd| <= half a bf16 ulp: the same bound as round-to-nearest bf16.
+__device__ __forceinline__ uint32_t pack_pair_fused(float even, float odd) {
+    const uint32_t lo = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(even));
+    const uint32_t ob = __float_as_uint(odd);
+    const uint32_t sign = ob & 0x80000000u;
+    long long m = (long long)(ob & 0x7fffffffu) - (long long)lo + 32768;  // magnitudes order like integers
+    if (m < 0) m = 0;
+    uint32_t mag = ((uint32_t)m & 0xffff0000u) | lo;
+    if (mag >= 0x7f800000u) mag = 0x7f7f0000u | lo;  // never round into inf/nan
+    return sign | mag;
+}
+
+// Optional kernel timeline (OZ_NET_TRACE=<slots>): every CTA folds its start / end %globaltimer into the launch's slot;
+// the table is printed to stderr when the engine is destroyed (tools/trace_forward.py).
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_begin(unsigned long long* slot) {
+    if (slot && threadIdx.x == 0) atomicMin(slot, global_ns());
+}
+__device__ __forceinline__ void trace_end(unsigned long long* slot) {
+    if (slot && threadIdx.x == 0) atomicMax(slot + 1, global_ns());
+}
+
 template <int BLOCK_N>
 struct GemmSmem {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -195,6 +225,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     float* s_bias = (float*)(gbase + S::OFF_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    trace_begin(p.trace);
     int L = *p.count;
     if (L > p.max_count) L = p.max_count;
     const int m_tiles = (L * p.tile_num + p.tile_den - 1) / p.tile_den;
@@ -309,8 +340,12 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int j = 0; j < 16; ++j) {
                             float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], LO);
                             float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], LO);
-                            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                            if constexpr (EPI == EPI_LINEAR_BF16) {
+                                packed[j] = pack_pair_fused(a, b);
+                            } else {
+                                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                            }
                         }
                         uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
@@ -362,6 +397,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    trace_end(p.trace);
 }
 
 // ---- 2-CTA variant: cta_group::2, one 256 x 256 accumulator tile per SM pair ---------------------------------
@@ -448,6 +484,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    trace_begin(p.trace);
     int L = *p.count;
     if (L > p.max_count) L = p.max_count;
     const int m_tiles = (L * p.tile_num + p.tile_den - 1) / p.tile_den;
@@ -584,6 +621,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, TMEM_COLS);
     }
+    trace_end(p.trace);
 }
 
 // ---- conv1 as a table gather -------------------------------------------------------------------------
@@ -668,23 +706,29 @@ __global__ void permute_conv2_weights_kernel(const bf16* __restrict__ w /*[co][t
     }
 }
 
+// One warp per output square: NJ x 9 independent 16-byte loads per lane (the whole 1-KB row of every tap), fp32x2
+// accumulation.  Measured alternatives (B200, 4096 boards, C=512): half-row warp items at 62 registers / 32 warps per SM
+// are SLOWER (0.28 vs 0.19 ms: the per-item address arithmetic doubles); masking the odd element instead of the fused
+// pair encoding costs 20 % more instructions for the same time (the kernel is latency-, not issue-bound at 62 % issue).
 template <int NJ>  // 16-byte chunks per lane: C = 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
 __global__ void __launch_bounds__(256, 2)
 conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count,
                           int max_count, int n, int C, const bf16* __restrict__ table2, const float* __restrict__ bias,
-                          bf16* __restrict__ out) {
+                          bf16* __restrict__ out, unsigned long long* trace) {
     __shared__ int s_pat[100];  // (n+2) x (n+2) patterns with a border of N_PATTERNS (the zero row)
+    trace_begin(trace);
     int L = *count;
     if (L > max_count) L = max_count;
     const int nsq = n * n, np2 = n + 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cpr = C >> 3;  // 16-byte chunks per row
-    float bs[NJ][8];
+    float2 bs[NJ][4];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int ch = lane + 32 * j;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bs[j][i] = ch < cpr ? bias[ch * 8 + i] : 0.f;
+        for (int i = 0; i < 4; ++i)
+            bs[j][i] = ch < cpr ? make_float2(bias[ch * 8 + 2 * i], bias[ch * 8 + 2 * i + 1]) : make_float2(0.f, 0.f);
     }
     const uint4* tab = reinterpret_cast<const uint4*>(table2);
     for (int b = blockIdx.x; b < L; b += gridDim.x) {
@@ -727,22 +771,20 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
             bf16* orow = out + ((size_t)b * nsq + pos) * C;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
-                float acc[8];
+                float2 acc[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = bs[j][i];
+                for (int i = 0; i < 4; ++i) acc[i] = bs[j][i];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const uint32_t w4[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        acc[2 * i] += __uint_as_float(w4[i] << 16);
-                        acc[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
-                    }
+                    for (int i = 0; i < 4; ++i)  // (even, odd) = (low half << 16, the word itself: see pack_pair_fused)
+                        acc[i] = __fadd2_rn(acc[i], make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i])));
                 }
                 uint32_t pk[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f));
+                    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
                     pk[i] = *reinterpret_cast<uint32_t*>(&h);
                 }
                 const int ch = lane + 32 * j;
@@ -751,6 +793,7 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
         }
         __syncthreads();
     }
+    trace_end(trace);
 }
 
 // ---- weight folding -------------------------------------------------------------------------------------
@@ -824,6 +867,9 @@ struct OzNet {
     bool conv2_table = true;
     bf16* table2 = nullptr; bf16* w2perm = nullptr; float* zero_bias = nullptr; int* d_npat = nullptr;
     OzLayer tbl;
+    unsigned long long* trace = nullptr;  // OZ_NET_TRACE: [trace_slots][2]
+    int trace_slots = 0, trace_next = 0;
+    char trace_name[256][12];
     bf16 *w[6] = {nullptr}; float* bias[6] = {nullptr};  // conv2, conv3, conv4, fc1, fc2, heads
     bf16 *act1 = nullptr, *act2 = nullptr, *act3 = nullptr, *act4 = nullptr, *f1 = nullptr, *f2 = nullptr;
     OzLayer layer[6];
@@ -880,6 +926,8 @@ int oz_net_create(oz_engine* e) {
     net->pdl = !(pd && pd[0] == '1');
     const char* c2 = getenv("OZ_NET_CONV2");
     net->conv2_table = !(c2 && c2[0] == 'g');
+    const char* tr = getenv("OZ_NET_TRACE");
+    if (tr && atoi(tr) > 0) net->trace_slots = atoi(tr) > 256 ? 256 : atoi(tr);
     const char* te = getenv("OZ_NET_TIMING_EVERY");
     if (te && atoi(te) > 0) net->timing_every = atoi(te);
     int dev = e->cfg.device;
@@ -890,9 +938,29 @@ int oz_net_create(oz_engine* e) {
     return OZ_OK;
 }
 
+static unsigned long long* trace_slot(OzNet* net, const char* name) {
+    if (!net->trace || net->trace_next >= net->trace_slots) return nullptr;
+    snprintf(net->trace_name[net->trace_next], sizeof(net->trace_name[0]), "%s", name);
+    return net->trace + 2 * (net->trace_next++);
+}
+
+static void trace_dump(OzNet* net) {
+    if (!net->trace || net->trace_next == 0) return;
+    cudaDeviceSynchronize();
+    unsigned long long* h = (unsigned long long*)malloc(sizeof(unsigned long long) * 2 * net->trace_next);
+    cudaMemcpy(h, net->trace, sizeof(unsigned long long) * 2 * net->trace_next, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int i = 0; i < net->trace_next; ++i) if (h[2 * i] < t0) t0 = h[2 * i];
+    for (int i = 0; i < net->trace_next; ++i)
+        fprintf(stderr, "OZ_TRACE %3d %-8s start %9.1f us  end %9.1f us  dur %8.1f us\n", i, net->trace_name[i],
+                (h[2 * i] - t0) / 1e3, (h[2 * i + 1] - t0) / 1e3, (h[2 * i + 1] - h[2 * i]) / 1e3);
+    free(h);
+}
+
 void oz_net_destroy(oz_engine* e) {
     OzNet* net = e->net;
     if (!net) return;
+    trace_dump(net);
     for (int i = 0; i < net->n_allocs; ++i) cudaFree(net->allocs[i]);
     for (int r = 0; r < OzNet::RING; ++r)
         for (int i = 0; i < 8; ++i) if (net->ev[r][i]) cudaEventDestroy(net->ev[r][i]);
@@ -1004,6 +1072,11 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         NA(net->act1, (size_t)B * nsq * C * 2) NA(net->act2, (size_t)B * nsq * C * 2)
         NA(net->act3, (size_t)B * o2 * o2 * C * 2) NA(net->act4, (size_t)B * o4 * o4 * C * 2)
         NA(net->f1, (size_t)B * 1024 * 2) NA(net->f2, (size_t)B * 512 * 2)
+        if (net->trace_slots) {
+            NA(net->trace, (size_t)net->trace_slots * 16)
+            OZ_CUDA(cudaMemsetAsync(net->trace, 0, (size_t)net->trace_slots * 16, st));
+            for (int i = 0; i < net->trace_slots; ++i) OZ_CUDA(cudaMemsetAsync(net->trace + 2 * i, 0xff, 8, st));
+        }
         if (net->conv2_table) {
             NA(net->table2, (size_t)(N_PATTERNS + 1) * 9 * C * 2) NA(net->w2perm, kc * 2)
             NA(net->zero_bias, 9ull * C * 4) NA(net->d_npat, 16)
@@ -1023,6 +1096,8 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
                                   9 * C, 256, EPI_LINEAR_BF16, net->table2, 9 * C))) return rc;
             OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<256, EPI_LINEAR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmSmem<256>::DYN_BYTES));
+            OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_LINEAR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmSmem<128>::DYN_BYTES));
             OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_LINEAR_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmSmem<128>::DYN_BYTES));
             OZ_CUDA(cudaMemsetAsync(net->table2 + (size_t)N_PATTERNS * 9 * C, 0, 9ull * C * 2, st));  // the padding row
@@ -1144,12 +1219,15 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
     if (net->conv2_table) {  // conv1 + conv2 in one gather-sum over the partial-product table
         int blocks = max_count < net->sm_count * 2 ? max_count : net->sm_count * 2;  // 2 resident CTAs/SM, grid-stride
         const bf16* t2 = net->table2; const float* b2 = net->bias[0];
+        unsigned long long* ts = trace_slot(net, "gather");
+#define OZ_T2(NJ) conv2_table_gather_kernel<NJ><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2, ts)
         switch (C / 256) {
-            case 0: case 1: conv2_table_gather_kernel<1><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
-            case 2: conv2_table_gather_kernel<2><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
-            case 3: conv2_table_gather_kernel<3><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
-            default: conv2_table_gather_kernel<4><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2); break;
+            case 0: case 1: OZ_T2(1); break;
+            case 2: OZ_T2(2); break;
+            case 3: OZ_T2(3); break;
+            default: OZ_T2(4); break;
         }
+#undef OZ_T2
         OZ_CUDA(cudaGetLastError());
         e->launches++;
         if (tm) cudaEventRecord(ev[2], st);
@@ -1159,6 +1237,8 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         GemmParams p = Lr.p;
         p.count = count_dev;
         p.max_count = max_count;
+        static const char* lname[6] = {"conv2", "conv3", "conv4", "fc1", "fc2", "heads"};
+        p.trace = trace_slot(net, lname[li]);
         p.pi = pi_dev; p.logits = logits_dev; p.v = v_dev;
         int tiles = ((max_count * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
         int grid = tiles < net->sm_count ? tiles : net->sm_count;
