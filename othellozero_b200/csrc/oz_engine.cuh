@@ -68,6 +68,8 @@ struct OzTreeParams {
     int* pend_parent; int* pend_edge; int* pend_depth; int* pend_leaf;  // [G][vl_width]
     int* pend_count;                                                     // [G] leaves of the current wave
     int vl_width;                                                        // 1 = sequential (bit-exact) mode
+    int sim_budget;  // self-play with an evaluator: simulations a game may complete per launch WITHOUT needing the evaluator
+                     // (terminal visits, evaluation-cache hits) before it yields to the next step; 0 = unbounded
     u32* path_node; u32* path_edge;  // [G][vl_width][64]
     // pools
     unsigned char* arena; u64 arena_stride;  // bytes per game

@@ -405,7 +405,12 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
     int player = P.player[slot];
     int ply = P.ply[slot];
 
+    int ran = 0;  // simulations completed by this launch without the evaluator
     while (true) {
+        if (P.selfplay && P.sim_budget > 0 && ran >= P.sim_budget) {  // yield: see oz_tree_alloc
+            status = inflight > 0 ? OZ_GAME_WAIT_LEAF : OZ_GAME_ACTIVE;
+            break;
+        }
         if (sims_left - inflight <= 0) {
             if (inflight > 0) { status = OZ_GAME_WAIT_LEAF; break; }
             if (!P.selfplay) { status = OZ_GAME_IDLE; break; }
@@ -559,7 +564,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
         }
         if (outcome == 1) {
             backup_path(arena, path, lane, depth, true, term_val, (float)term_val, vl);
-            ++c_term; ++c_sims;
+            ++c_term; ++c_sims; ++ran;
             --sims_left;
             continue;
         }
@@ -598,7 +603,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
                     status = OZ_GAME_POOL_FULL;
                     break;
                 }
-                ++c_nodes; ++c_sims; ++c_hits;
+                ++c_nodes; ++c_sims; ++c_hits; ++ran;
                 --sims_left;
                 continue;
             }
@@ -731,6 +736,12 @@ int oz_tree_alloc(oz_engine* e) {
     OzTreeParams& P = e->tp;
     const int V = e->cfg.vl_width > 1 ? e->cfg.vl_width : 1;
     P.vl_width = V;
+    // Endgame trees are mostly terminal edges: a game can run hundreds of simulations back to back without needing the
+    // network while every other game waits for the launch to end (measured: 2 ms tree launches for ~1000 evaluations per
+    // step over the last ten plies).  Bounding the run lets the step turn around; per-game results are unchanged (the
+    // game resumes at the same simulation in the next launch).
+    P.sim_budget = (e->cfg.prior_mode == OZ_PRIOR_NET || V > 1) ? 8 : 0;  // measured: 4-16 equal, 64 and unbounded slower
+    if (const char* sb = getenv("OZ_TREE_SIM_BUDGET")) P.sim_budget = atoi(sb) > 0 ? atoi(sb) : 0;
     e->max_leaves = G * V;
     const size_t GV = (size_t)G * V;
     P.n = e->cfg.board_size;
