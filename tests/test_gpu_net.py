@@ -209,3 +209,29 @@ def test_config0_6x6_25sims_c512_episode():
         assert got == ref["visits"][p].tolist()
     assert int(out["winner"][0]) == ref["winner"]
     e.close()
+
+
+def test_sim_budget_is_results_preserving(monkeypatch):
+    """The tree kernel yields after OZ_TREE_SIM_BUDGET evaluator-free simulations per launch (terminal visits, cache
+    hits); where a game pauses must not change anything it plays or counts."""
+    from othellozero_b200 import engine, net
+    n, C, sims, G = 6, 128, 20, 48
+    blob = net.init_weights(n, C, seed=13, randomize_bn=True)
+    ids = np.arange(G, dtype=np.uint64) + 500
+    outs, steps = [], []
+    for budget in ("0", "1", "8"):
+        monkeypatch.setenv("OZ_TREE_SIM_BUDGET", budget)
+        e = engine.Engine(n, max_games=G, nodes_per_game=sims * 40, prior_mode=engine.PRIOR_NET, seed=9, log_visits=True,
+                          eval_cache_log2=14)
+        e.load_weights(blob, C)
+        e.selfplay_begin(G, sims, 1.0, 0.9, -1, None, None, None, ids)
+        assert e.selfplay_run(-1) == 0
+        outs.append(e.selfplay_records())
+        c = e.counters()
+        steps.append((c["sims"], c["nodes"], c["terminal_visits"], c["moves"]))
+        e.close()
+    for o in outs[1:]:
+        for k in ("black", "white", "action", "player", "n_moves", "winner", "visits"):
+            assert np.array_equal(outs[0][k], o[k]), k
+    assert steps[0] == steps[1] == steps[2]
+    assert steps[0][2] > 0   # the endgames did visit terminal edges
