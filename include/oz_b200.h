@@ -168,7 +168,8 @@ int oz_selfplay_get_positions(oz_engine* e, uint64_t* black, uint64_t* white, in
 /* ---- network: NNetWrapper.predict / OthelloNN (Net/NNet.py:70-87, Net/OthelloNN.py:42-52) -- */
 /* Weights as one float32 HOST blob in Keras layer order (kernel HWIO / (in,out), bias, then BN gamma, beta,
  * moving_mean, moving_var for the six BN layers): see INTEGRATION.md for the exact order.  BN (eps 1e-3) is
- * folded, conv2..fc2 + heads are cast to bf16.  channels must be a multiple of 128. */
+ * folded, conv2..fc2 + heads are cast to bf16, and the conv1 / conv1∘conv2 lookup tables are rebuilt on the device
+ * (19683 x 9 x channels bf16, ~0.1 ms).  channels must be a multiple of 128. */
 int oz_net_load_weights(oz_engine* e, const float* blob, int64_t n_floats, int32_t channels);
 /* Same, from a DEVICE float32 blob (e.g. a tensor just received by ncclBroadcast). */
 int oz_net_load_weights_dev(oz_engine* e, const float* blob_dev, int64_t n_floats, int32_t channels);
@@ -180,13 +181,16 @@ int oz_net_forward_host(oz_engine* e, const uint64_t* own, const uint64_t* opp, 
 int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint64_t* opp, int32_t n, float* pi,
                        float* logits, float* v);
 /* Debug/inspection: raw bf16 activations of the last forward. layer 0..5 = conv1, conv2, conv3, conv4, fc1, fc2
- * outputs ([n][rows][channels] row-major); copies `bytes` bytes to the HOST buffer. */
+ * outputs ([n][rows][channels] row-major); copies `bytes` bytes to the HOST buffer.  conv1+conv2 normally run as one
+ * gather over a pre-computed partial-product table, which never materialises conv1's output: layer 0 then
+ * fails with OZ_ERR_STATE (engines created with OZ_NET_CONV2=gemm in the environment keep it). */
 int oz_net_get_activation(oz_engine* e, int32_t layer, void* host_bf16, int64_t bytes);
 /* Kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
 int oz_engine_launches(oz_engine* e, uint64_t* launches);
 /* Per-layer device timing with CUDA events on the engine stream (no host sync in the hot loop).
- * oz_net_layer_times: average ms per launch since the previous call for [0] conv1 gather, [1] conv2, [2] conv3,
- * [3] conv4, [4] fc1, [5] fc2, [6] heads; [7] = number of forwards averaged. */
+ * oz_net_layer_times: average ms per launch since the previous call for [0] conv1 gather (0 when conv1+conv2 run as
+ * the table gather), [1] conv2 (the table gather, or the implicit GEMM), [2] conv3, [3] conv4, [4] fc1, [5] fc2,
+ * [6] heads; [7] = number of forwards averaged. */
 int oz_net_set_timing(oz_engine* e, int32_t on);
 int oz_net_layer_times(oz_engine* e, float* ms8);
 

@@ -1,9 +1,12 @@
 // oz_net.cu — K7..K10: the OthelloNNet policy/value tower (Net/OthelloNN.py:42-52) as bf16 tcgen05 kernels.
 //
 //   conv1 (Cin=2)     : the 3x3x2 binary input patch has only 3^9 = 19683 states, so conv1+BN+ReLU is a
-//                       pre-computed 19683 x C bf16 table (built at weight load) and the layer is a pure
-//                       gather from the L2-resident table (K7 fused with conv1).  HBM-write bound.
-//   conv2..4, fc1, fc2: ONE persistent, warp-specialised implicit-GEMM kernel:
+//                       pre-computed 19683 x C bf16 table (built at weight load).
+//   conv1∘conv2       : conv2 is linear in conv1's output, so tap t of conv2 applied to table row p is again a
+//                       table: table2[p][t][:] (19683 x 9 x C bf16, built by the GEMM kernel at weight load) and
+//                       the two layers are ONE gather-sum kernel (<= 9 row reads per output square), see
+//                       conv2_table_gather_kernel.  OZ_NET_CONV2=gemm keeps conv1 = gather, conv2 = implicit GEMM.
+//   conv3..4, fc1, fc2: ONE persistent, warp-specialised implicit-GEMM kernel:
 //                       TMA (4-D tiled tensor map over the NHWC activation; taps = shifted boxes with
 //                       hardware zero fill for padding='same') -> 128B-swizzled smem ring ->
 //                       tcgen05.mma (128 x BLOCK_N x 16, bf16 in / fp32 accumulate in TMEM, double
