@@ -406,14 +406,46 @@ def run_ours(args):
     print(json.dumps(out))
 
 
+PERFT_THREAD_INSTR_PER_PLY = 624     # counted by ncu on perft_playout_kernel (profiles/r1_ncu_perft_raw.csv): 1.51e9 warp
+                                     # instructions x 32 lanes / 7.7e7 plies of one 1M-game launch
+
+
+def _perft_cpu_worker(a):
+    wid, games, seed = a
+    import oracle
+    t0 = time.perf_counter()
+    plies = 0
+    for g in range(games):
+        plies += len(oracle.playout(8, seed, wid * games + g)["moves"])
+    return plies, time.perf_counter() - t0
+
+
+def perft_cpu_sample(games_per_proc=4000, procs=None):
+    """CPU arm of configs[1]: the oracle's C restatement of OthelloGame.play driven by the same counter RNG
+    (RandomOthelloAgent loop, agents.py:20-24,71-84), one process per host core."""
+    import multiprocessing as mp
+    import oracle
+    oracle.build()
+    procs = procs or min(os.cpu_count() or 1, 32)
+    with mp.get_context("spawn").Pool(procs) as pool:
+        pool.map(_perft_cpu_worker, [(w, 10, 1) for w in range(procs)])  # warm: imports
+        t0 = time.perf_counter()
+        res = pool.map(_perft_cpu_worker, [(w, games_per_proc, 0) for w in range(procs)])
+        wall = time.perf_counter() - t0
+    plies = sum(r[0] for r in res)
+    return dict(value=plies / wall, unit="plies/s", cores=procs, kind="port",
+                sample=f"{procs} processes x {games_per_proc} random 8x8 playouts through the oracle's OthelloGame.play "
+                       f"restatement: {plies} plies in {wall:.1f}s")
+
+
 def run_perft(args, E, peaks, rank, world, local, barrier):
+    import ctypes as C
     import torch
     n_games = args.games if args.games > 4096 else (1 << 20)
     b = torch.empty(n_games, dtype=torch.int64, device=f"cuda:{local}")
     w = torch.empty_like(b)
     info = torch.empty(n_games, dtype=torch.int32, device=f"cuda:{local}")
     L = E._lib.load()
-    import ctypes as C
 
     def launch(seed):
         E.check(L.oz_perft_playouts_dev(8, seed, rank * n_games, n_games, -1, C.c_void_p(b.data_ptr()),
@@ -421,27 +453,78 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
     for i in range(args.warmup):
         launch(i)
     barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    plies = 0
     ev0.record()
     for i in range(args.steps):
         launch(100 + i)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    plies = int((info & 0xFF).sum().item()) * args.steps  # plies of the last launch x steps (same distribution)
-    if rank == 0:
-        print(json.dumps({"metric": "perft_plies_per_sec", "value": plies / (ms / 1e3) * world, "unit": "plies/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-                          "data": "synthetic", "config": {"workload": "8x8 random-playout perft, %d concurrent games per GPU "
-                                                                    "(BASELINE.json configs[1])" % n_games},
-                          "gpu_launches": args.steps}))
+    clocks = sampler.stop() if rank == 0 else None
+    # every launch plays different games (seed): replay the same seeds outside the timed region to count their plies
+    plies = 0
+    for i in range(args.steps):
+        launch(100 + i)
+        plies += int((info & 0xFF).sum().item())
+    # e2e: the host-buffer entry point (results D2H inside the timed region), one launch
+    t0 = time.perf_counter()
+    out = E.perft_playouts(n_games, 8, seed=7, first_game_id=rank * n_games, device=local)
+    dt = time.perf_counter() - t0
+    e_plies = int(out["plies"].sum())
+    t = torch.tensor([ms, float(plies), dt, float(e_plies)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+        tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        ms, dt, plies, e_plies = float(tm[0]), float(tm[2]), int(ts[1]), int(ts[3])
+        dist.barrier(); dist.destroy_process_group()
+    if rank != 0:
+        return
+    value = plies / (ms / 1e3)
+    f_sm = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 4 * 32 * f_sm * 1e6 / 1e9          # thread-instructions / ns the SMs can issue at the sampled clock
+    achieved = value / world * PERFT_THREAD_INSTR_PER_PLY / 1e9
+    line = {"metric": "perft_plies_per_sec", "value": value, "unit": "plies/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "8x8 random-playout perft, %d concurrent games per GPU (BASELINE.json configs[1])" % n_games,
+                       "l2": "state lives in registers for the whole game; 24 B written per game"},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": {"bound": "int-issue", "kernel": "perft_playout_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "G thread-instr/s", "frac": achieved / peak, "traffic": None,
+                         "note": "SURVEY 8d: the path is integer-issue bound, not HBM bound; achieved = plies/s x 624 counted "
+                                 "thread-instructions per ply, peak = 148 SMs x 4 schedulers x 32 lanes x sampled SM clock; "
+                                 "ncu: ALU pipe 95.6 % active (profiles/r1_ncu_perft_raw.csv)"},
+            "e2e": {"value": e_plies / dt, "unit": "plies/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(n_games * 20), "what": "oz_perft_playouts_host: one launch + final boards/info D2H"}}
+    if not args.no_cpu:
+        line["cpu_baseline"] = perft_cpu_sample()
+    print(json.dumps(line))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload == "perft":
+        vals, last = [], None
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            last = perft_cpu_sample(games_per_proc=2000)
+            vals.append(last["value"])
+        dt = time.perf_counter() - t0
+        v = float(np.mean(vals)); last["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "perft_plies_per_sec", "value": v, "unit": "plies/s",
+                          "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": dt / max(1, args.steps) * 1e3, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "8x8 random-playout perft (BASELINE.json configs[1]); CPU arm = oracle port of "
+                                                 "OthelloGame.play on all host cores"},
+                          "cpu_baseline": last,
+                          "e2e": {"value": v, "unit": "plies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     arm = CpuArm(8, args.channels)
     try:
