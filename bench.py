@@ -373,6 +373,12 @@ def run_ours(args):
             k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm_kernel<256,relu> (conv3 implicit GEMM, split M tiles)"
             traffic = ncu_traffic("oz_gemm_kernel<256, 0>", "r1_ncu_t2_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
             tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8 - FLOP_CONV2_PER_BOARD_8
+            if args.conv3 == "wino":
+                # F(2,3) along y: 4 GEMMs with K = 3C instead of one with 9C -> 2/3 of the direct form's MACs are EXECUTED
+                k_flop = FLOP_CONV3_PER_BOARD_8 * 2 // 3
+                k_name = "oz_wino_kernel (conv3 as 1-D Winograd F(2,3), SM pair; executed FLOPs = 2/3 of the direct form)"
+                traffic = ncu_traffic("oz_wino_kernel", "r1_ncu_wino_raw.csv", 4096 * (96 + 36) * 512 * 2 + 12 * 512 * 512 * 2)
+                tensor_flop_per_eval -= FLOP_CONV3_PER_BOARD_8 // 3
         else:
             k_ms, k_flop, k_name = float(lt[1]), FLOP_CONV2_PER_BOARD_8, "oz_gemm2_kernel (conv2 implicit GEMM, SM pair)"
             traffic = ncu_traffic("oz_gemm_kernel<256, 0>")
@@ -572,6 +578,8 @@ def main():
     ap.add_argument("--eval-cache-log2", type=int, default=24)
     ap.add_argument("--conv2", default="table", choices=["table", "gemm"],
                     help="conv2 as the conv1∘conv2 partial-product table gather (default) or as the tcgen05 implicit GEMM")
+    ap.add_argument("--conv3", default="direct", choices=["direct", "wino"],
+                    help="conv3 as the direct implicit GEMM (default) or as the opt-in Winograd F(2,3) kernel (DESIGN 3b)")
     ap.add_argument("--vl", type=int, default=1, help="virtual-loss wave width (configs[3]); 1 = sequential, bit-exact")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -579,6 +587,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     os.environ["OZ_NET_CONV2"] = args.conv2  # read by the engine when it is created
+    os.environ["OZ_NET_CONV3"] = args.conv3 if args.conv2 == "table" else "direct"
     return run_ours(args)
 
 

@@ -183,7 +183,8 @@ int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint64_t* opp, i
 /* Debug/inspection: raw bf16 activations of the last forward. layer 0..5 = conv1, conv2, conv3, conv4, fc1, fc2
  * outputs ([n][rows][channels] row-major); copies `bytes` bytes to the HOST buffer.  conv1+conv2 normally run as one
  * gather over a pre-computed partial-product table, which never materialises conv1's output: layer 0 then
- * fails with OZ_ERR_STATE (engines created with OZ_NET_CONV2=gemm in the environment keep it). */
+ * fails with OZ_ERR_STATE (engines created with OZ_NET_CONV2=gemm in the environment keep it); likewise layer 1 with the
+ * opt-in OZ_NET_CONV3=wino (conv3 as a Winograd F(2,3) kernel fed by the gather's input transform). */
 int oz_net_get_activation(oz_engine* e, int32_t layer, void* host_bf16, int64_t bytes);
 /* Kernel launches issued by this engine since creation (bench.py "gpu_launches"). */
 int oz_engine_launches(oz_engine* e, uint64_t* launches);

@@ -145,6 +145,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // Programmatic dependent launch: let the next layer's CTAs start their prologue as ours retire, and make our own
@@ -627,6 +635,254 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     trace_end(p.trace);
 }
 
+// ---- conv3 as a 1-D Winograd F(2,3) along y, on SM pairs -------------------------------------------------------------
+// A 'valid' 3x3 convolution produces output rows (2ty, 2ty+1) from input rows d0..d3 = 2ty..2ty+3.  With
+//     V0 = d0-d2, V1 = d1+d2, V2 = d2-d1, V3 = d1-d3               (input transform: done by the table gather, bf16)
+//     U0 = g0, U1 = (g0+g1+g2)/2, U2 = (g0-g1+g2)/2, U3 = g2         (filter transform over ky: done at weight load)
+//     M_e[b,ty,x][co] = sum_{kx,ci} V_e[b,ty,x+kx][ci] * U_e[co][kx,ci]            (4 GEMMs with K = 3C instead of one with 9C)
+//     out[2ty] = M0 + M1 + M2,  out[2ty+1] = M1 - M2 - M3
+// the layer needs 2/3 of the tensor-core work of the direct form (4 x 3 instead of 2 x 9 channel contractions per output
+// pair).  M0..M3 of a tile must meet in one epilogue, so the four accumulators (128 fp32 columns each) fill the 512 TMEM
+// columns of the SM; the MMA/epilogue overlap that double buffering gave the direct kernel is recovered differently: the
+// epilogue first copies M0 into registers and releases accumulator 0, so the next tile's e=0 MMAs (a quarter of its main
+// loop) run while this tile's outputs are combined and stored.  Rows of an M tile are (board, ty, x): 18 per 8x8 board,
+// 7 boards = 126 of 128 rows.  Same SM-pair scheme as oz_gemm2_kernel (each CTA stages its 128 A rows and its 64-row half
+// of the 128-row B tile: 24 KB per k-block, 8-deep ring).
+constexpr int WSTAGES = 8;
+constexpr int WINO_N = 128;
+constexpr int WB_STAGE_BYTES = (WINO_N / 2) * BLOCK_K * 2;
+constexpr int WINO_THREADS = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..11 epilogue (two column halves per TMEM lane quarter)
+struct WinoSmem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = WSTAGES * A_STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_B + WSTAGES * WB_STAGE_BYTES;  // full[S], empty[S], tfull, tempty0, tempty123
+    static constexpr int OFF_TMEM = OFF_BAR + (2 * WSTAGES + 4) * 8;
+    static constexpr int OFF_BIAS = OFF_TMEM + 16;                    // [2][WINO_N] floats
+    static constexpr int BYTES = OFF_BIAS + 2 * WINO_N * 4;
+    static constexpr int DYN_BYTES = BYTES + 1024;
+};
+struct WinoParams {
+    int num_kb_eta;      // 3 * C / 64: k-blocks of one transformed GEMM
+    int chunks_per_tap;  // C / 64
+    int nb;              // boards per M tile
+    int rows_per_board;  // T * OW
+    int rows_valid;      // nb * rows_per_board
+    int OW, OH;          // output width / height (n-2)
+    int n_tiles;         // C / 128
+    int C;
+    int bmax;            // boards per eta slab of V
+    int max_count;
+    unsigned a_bytes;
+    const int* count;
+    const float* bias;
+    bf16* out;           // act3 [B][OH][OW][C]
+    unsigned long long* trace;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WINO_THREADS, 1)
+oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapU, const WinoParams p) {
+    using S = WinoSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + S::OFF_A, sB = base + S::OFF_B, sBar = base + S::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (WSTAGES + s); };
+    const uint32_t tfull_bar = sBar + 8u * (2 * WSTAGES);
+    const uint32_t tempty0_bar = sBar + 8u * (2 * WSTAGES + 1);   // accumulator 0 has been copied out
+    const uint32_t tempty1_bar = sBar + 8u * (2 * WSTAGES + 2);   // accumulators 1..3 have been drained
+    volatile uint32_t* s_tmem = (volatile uint32_t*)(gbase + S::OFF_TMEM);
+    float* s_bias = (float*)(gbase + S::OFF_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    trace_begin(p.trace);
+    int L = *p.count;
+    if (L > p.max_count) L = p.max_count;
+    const int m_tiles = (L + p.nb - 1) / p.nb;
+    const int num_pair_tiles = ((m_tiles + 1) >> 1) * p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapV);
+        tma_prefetch_desc(&mapU);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty0_bar, 16);  // 8 epilogue warps x 2 CTAs
+        mbar_init(tempty1_bar, 16);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc_2sm(smem_u32((const void*)s_tmem), 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs; bytes land on the leader's full barrier) =====
+            pdl_wait();
+            int stage = 0; uint32_t phase = 0;
+            for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+                const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
+                const int m_tile = 2 * m_pair + (int)rank;
+                for (int eta = 0; eta < 4; ++eta) {
+                    for (int kb = 0; kb < p.num_kb_eta; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t fb = mapa_cluster(full_bar(stage), 0);
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (p.a_bytes + (unsigned)WB_STAGE_BYTES));
+                        const int kx = kb / p.chunks_per_tap, chunk = kb - kx * p.chunks_per_tap;
+                        tma_load_4d_2sm(sA + stage * A_STAGE_BYTES, &mapV, fb, chunk * BLOCK_K, kx, 0,
+                                        eta * p.bmax + m_tile * p.nb);
+                        tma_load_2d_2sm(sB + stage * WB_STAGE_BYTES, &mapU, fb, kb * BLOCK_K,
+                                        eta * p.C + n_idx * WINO_N + (int)rank * (WINO_N / 2));
+                        if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA) =====
+            constexpr uint32_t idesc = make_idesc(256, WINO_N);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t tile_phase = 0;
+            for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+                for (int eta = 0; eta < 4; ++eta) {
+                    if (eta == 0) { mbar_wait(tempty0_bar, tile_phase ^ 1u); tc_fence_after(); }
+                    if (eta == 1) { mbar_wait(tempty1_bar, tile_phase ^ 1u); tc_fence_after(); }
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(eta * WINO_N);
+                    for (int kb = 0; kb < p.num_kb_eta; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
+                        const uint64_t bdesc = make_sw128_desc(sB + stage * WB_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        umma_commit_2sm(empty_bar(stage), 3);
+                        if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit_2sm(tfull_bar, 3);  // all four accumulators complete -> both epilogues
+                tile_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: out[2ty] = M0+M1+M2, out[2ty+1] = M1-M2-M3 (+bias, ReLU, bf16) =====
+        const int ew = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;  // which 64 of the 128 columns
+        const int et = threadIdx.x - 128;
+        uint32_t tile_phase = 0;
+        int buf = 0;
+        for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
+            const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
+            const int m_tile = 2 * m_pair + (int)rank;
+            float* bias = s_bias + buf * WINO_N;
+            if (et < WINO_N) bias[et] = p.bias[n_idx * WINO_N + et];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int r = ew * 32 + lane;
+            const int bl = r / p.rows_per_board, rem = r - bl * p.rows_per_board;
+            const int ty = rem / p.OW, xo = rem - ty * p.OW;
+            const int b = m_tile * p.nb + bl;
+            const bool ok = (r < p.rows_valid) && (b < L);
+            bf16* out0 = p.out + (((long long)b * p.OH + 2 * ty) * p.OW + xo) * p.C + n_idx * WINO_N + half * 64;
+            bf16* out1 = out0 + (long long)p.OW * p.C;
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(half * 64);
+            mbar_wait(tfull_bar, tile_phase);
+            tc_fence_after();
+            uint32_t m0a[32], m0b[32];
+            tmem_ld32(t_row, m0a);
+            tmem_ld32(t_row + 32u, m0b);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty0_bar, 0));  // the next tile's e=0 MMAs may start
+            const float* bh = bias + half * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t m1[16], m2[16], m3[16];
+                tmem_ld16(t_row + (uint32_t)(1 * WINO_N + c * 16), m1);
+                tmem_ld16(t_row + (uint32_t)(2 * WINO_N + c * 16), m2);
+                tmem_ld16(t_row + (uint32_t)(3 * WINO_N + c * 16), m3);
+                tmem_ld_wait();
+                uint32_t pk0[8], pk1[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float y0[2], y1[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = c * 16 + 2 * j + h;
+                        const float a0 = __uint_as_float(col < 32 ? m0a[col & 31] : m0b[col & 31]);
+                        const float a1 = __uint_as_float(m1[2 * j + h]), a2 = __uint_as_float(m2[2 * j + h]);
+                        const float a3 = __uint_as_float(m3[2 * j + h]);
+                        const float bb = bh[col];
+                        y0[h] = fmaxf(__fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), bb), 0.0f);
+                        y1[h] = fmaxf(__fadd_rn(__fsub_rn(__fsub_rn(a1, a2), a3), bb), 0.0f);
+                    }
+                    __nv_bfloat162 h0 = __floats2bfloat162_rn(y0[0], y0[1]);
+                    __nv_bfloat162 h1 = __floats2bfloat162_rn(y1[0], y1[1]);
+                    pk0[j] = *reinterpret_cast<uint32_t*>(&h0);
+                    pk1[j] = *reinterpret_cast<uint32_t*>(&h1);
+                }
+                if (ok) {
+                    uint4* d0 = reinterpret_cast<uint4*>(out0 + c * 16);
+                    uint4* d1 = reinterpret_cast<uint4*>(out1 + c * 16);
+                    d0[0] = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+                    d0[1] = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
+                    d1[0] = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+                    d1[1] = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_cluster(tempty1_bar, 0));
+            tile_phase ^= 1u;
+            buf ^= 1;
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+    trace_end(p.trace);
+}
+
+// U[e][co][kx*C + ci] = bf16 of the F(2,3) filter transform over ky of the BN-folded conv kernel (Keras HWIO W[(ky*3+kx)*C+ci][co])
+__global__ void wino_weights_kernel(const float* __restrict__ W, const float* __restrict__ gamma, const float* __restrict__ var,
+                                    float eps, int C, bf16* __restrict__ U) {
+    const size_t per_eta = (size_t)C * 3 * C, total = 4 * per_eta;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int eta = (int)(i / per_eta);
+        const size_t r = i - (size_t)eta * per_eta;
+        const int co = (int)(r / (3 * C)), k = (int)(r - (size_t)co * 3 * C);
+        const int kx = k / C, ci = k - kx * C;
+        const float s = gamma[co] / sqrtf(var[co] + eps);
+        const float g0 = W[((size_t)(0 * 3 + kx) * C + ci) * C + co] * s;
+        const float g1 = W[((size_t)(1 * 3 + kx) * C + ci) * C + co] * s;
+        const float g2 = W[((size_t)(2 * 3 + kx) * C + ci) * C + co] * s;
+        float u;
+        if (eta == 0) u = g0;
+        else if (eta == 1) u = __fmul_rn(__fadd_rn(__fadd_rn(g0, g1), g2), 0.5f);
+        else if (eta == 2) u = __fmul_rn(__fadd_rn(__fsub_rn(g0, g1), g2), 0.5f);
+        else u = g2;
+        U[i] = __float2bfloat16(u);
+    }
+}
+
 // ---- conv1 as a table gather -------------------------------------------------------------------------
 // table[pattern][co] = relu(b' + sum_t [s_t==own] W'[t][0][co] + [s_t==opp] W'[t][1][co]), pattern = sum s_t 3^t,
 // t = ky*3+kx (cross-correlation, Keras Conv2D), s = 0 empty / outside the board (zero padding), 1 own, 2 opp.
@@ -713,11 +969,67 @@ __global__ void permute_conv2_weights_kernel(const bf16* __restrict__ w /*[co][t
 // accumulation.  Measured alternatives (B200, 4096 boards, C=512): half-row warp items at 62 registers / 32 warps per SM
 // are SLOWER (0.28 vs 0.19 ms: the per-item address arithmetic doubles); masking the odd element instead of the fused
 // pair encoding costs 20 % more instructions for the same time (the kernel is latency-, not issue-bound at 62 % issue).
-template <int NJ>  // 16-byte chunks per lane: C = 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
+template <int NJ>
+__device__ __forceinline__ void t2_square(const uint4* __restrict__ tab, const int* s_pat, int np2, int y, int x, int cpr,
+                                          int lane, const float2 (&bs)[NJ][4], uint4 (&res)[NJ]) {
+    uint4 v[9][NJ];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const int pat = s_pat[(y + t / 3) * np2 + (x + t % 3)];  // padded coordinates of (y+ky-1, x+kx-1)
+        const uint4* row = tab + ((size_t)pat * 9 + t) * cpr;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int ch = lane + 32 * j;
+            v[t][j] = ch < cpr ? __ldg(row + ch) : make_uint4(0, 0, 0, 0);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        float2 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = bs[j][i];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const uint32_t w4[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)  // (even, odd) = (low half << 16, the word itself: see pack_pair_fused)
+                acc[i] = __fadd2_rn(acc[i], make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i])));
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        res[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bf8_add(const uint4& a, const uint4& b) {
+    return make_uint4(bf2_add(a.x, b.x), bf2_add(a.y, b.y), bf2_add(a.z, b.z), bf2_add(a.w, b.w));
+}
+__device__ __forceinline__ uint4 bf8_sub(const uint4& a, const uint4& b) {
+    return make_uint4(bf2_sub(a.x, b.x), bf2_sub(a.y, b.y), bf2_sub(a.z, b.z), bf2_sub(a.w, b.w));
+}
+
+// WINO = false: writes act2 [B][n][n][C].
+// WINO = true : conv3 runs as the Winograd kernel above, so act2 itself is never stored; a warp walks one board column
+//               top to bottom, keeps the previous two (bf16-rounded) squares in registers and stores the input transform
+//               V [4][Bmax][T][n][C]:  V0 = d0-d2, V1 = d1+d2, V2 = d2-d1 when row 2ty+2 arrives, V3 = d1-d3 at row 2ty+3
+//               (bf16 subtraction of bf16 values: one rounding of the exact difference).
+template <int NJ, bool WINO>  // 16-byte chunks per lane: C = 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
 __global__ void __launch_bounds__(256, 2)
 conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count,
                           int max_count, int n, int C, const bf16* __restrict__ table2, const float* __restrict__ bias,
-                          bf16* __restrict__ out, unsigned long long* trace) {
+                          bf16* __restrict__ out, int bmax, unsigned long long* trace) {
     __shared__ int s_pat[100];  // (n+2) x (n+2) patterns with a border of N_PATTERNS (the zero row)
     trace_begin(trace);
     int L = *count;
@@ -758,40 +1070,54 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
             s_pat[threadIdx.x] = pat;
         }
         __syncthreads();
-        for (int pos = warp; pos < nsq; pos += 8) {
-            const int y = pos / n, x = pos - y * n;
-            uint4 v[9][NJ];
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int pat = s_pat[(y + t / 3) * np2 + (x + t % 3)];  // padded coordinates of (y+ky-1, x+kx-1)
-                const uint4* row = tab + ((size_t)pat * 9 + t) * cpr;
+        if constexpr (!WINO) {
+            for (int pos = warp; pos < nsq; pos += 8) {
+                const int y = pos / n, x = pos - y * n;
+                uint4 res[NJ];
+                t2_square<NJ>(tab, s_pat, np2, y, x, cpr, lane, bs, res);
+                uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)b * nsq + pos) * C);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int ch = lane + 32 * j;
-                    v[t][j] = ch < cpr ? __ldg(row + ch) : make_uint4(0, 0, 0, 0);
+                    if (ch < cpr) orow[ch] = res[j];
                 }
             }
-            bf16* orow = out + ((size_t)b * nsq + pos) * C;
+        } else {
+            const int T = (n - 2) >> 1;
+            const size_t eta_stride = (size_t)bmax * T * n * cpr;  // uint4 units
+            uint4* vout = reinterpret_cast<uint4*>(out);
+            for (int x = warp; x < n; x += 8) {
+                uint4 p2[NJ] = {}, p1[NJ] = {};
+#pragma unroll 1
+                for (int y = 0; y < n; ++y) {
+                    uint4 cur[NJ];
+                    t2_square<NJ>(tab, s_pat, np2, y, x, cpr, lane, bs, cur);
+                    if (y >= 2) {
+                        if (!(y & 1)) {
+                            const int ty = (y - 2) >> 1;
+                            uint4* v0 = vout + (((size_t)b * T + ty) * n + x) * cpr;
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) {
-                float2 acc[4];
+                            for (int j = 0; j < NJ; ++j) {
+                                const int ch = lane + 32 * j;
+                                if (ch < cpr) {
+                                    v0[ch] = bf8_sub(p2[j], cur[j]);
+                                    v0[eta_stride + ch] = bf8_add(p1[j], cur[j]);
+                                    v0[2 * eta_stride + ch] = bf8_sub(cur[j], p1[j]);
+                                }
+                            }
+                        } else {
+                            const int ty = (y - 3) >> 1;
+                            uint4* v3 = vout + 3 * eta_stride + (((size_t)b * T + ty) * n + x) * cpr;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = bs[j][i];
+                            for (int j = 0; j < NJ; ++j) {
+                                const int ch = lane + 32 * j;
+                                if (ch < cpr) v3[ch] = bf8_sub(p2[j], cur[j]);
+                            }
+                        }
+                    }
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const uint32_t w4[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)  // (even, odd) = (low half << 16, the word itself: see pack_pair_fused)
-                        acc[i] = __fadd2_rn(acc[i], make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i])));
+                    for (int j = 0; j < NJ; ++j) { p2[j] = p1[j]; p1[j] = cur[j]; }
                 }
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
-                    pk[i] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                const int ch = lane + 32 * j;
-                if (ch < cpr) reinterpret_cast<uint4*>(orow)[ch] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
         __syncthreads();
@@ -870,6 +1196,12 @@ struct OzNet {
     bool conv2_table = true;
     bf16* table2 = nullptr; bf16* w2perm = nullptr; float* zero_bias = nullptr; int* d_npat = nullptr;
     OzLayer tbl;
+    // conv3 as 1-D Winograd F(2,3): OZ_NET_CONV3=wino (needs conv2_table: the gather emits the input transform)
+    bool conv3_wino = false;
+    bf16* v3 = nullptr;      // [4][Bmax][T][n][C]
+    bf16* u3 = nullptr;      // [4][C][3C]
+    CUtensorMap mapV, mapU;
+    WinoParams wp;
     unsigned long long* trace = nullptr;  // OZ_NET_TRACE: [trace_slots][2]
     int trace_slots = 0, trace_next = 0;
     char trace_name[256][12];
@@ -929,6 +1261,8 @@ int oz_net_create(oz_engine* e) {
     net->pdl = !(pd && pd[0] == '1');
     const char* c2 = getenv("OZ_NET_CONV2");
     net->conv2_table = !(c2 && c2[0] == 'g');
+    const char* c3 = getenv("OZ_NET_CONV3");
+    net->conv3_wino = net->conv2_table && c3 && c3[0] == 'w';  // opt-in: measured at parity with the direct kernel
     const char* tr = getenv("OZ_NET_TRACE");
     if (tr && atoi(tr) > 0) net->trace_slots = atoi(tr) > 256 ? 256 : atoi(tr);
     const char* te = getenv("OZ_NET_TIMING_EVERY");
@@ -1072,7 +1406,8 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         NA(net->w[3], (size_t)K1 * 1024 * 2) NA(net->w[4], 1024ull * 512 * 2) NA(net->w[5], 128ull * 512 * 2)
         NA(net->bias[0], C * 4) NA(net->bias[1], C * 4) NA(net->bias[2], C * 4)
         NA(net->bias[3], 1024 * 4) NA(net->bias[4], 512 * 4) NA(net->bias[5], 128 * 4)
-        NA(net->act1, (size_t)B * nsq * C * 2) NA(net->act2, (size_t)B * nsq * C * 2)
+        NA(net->act1, (size_t)B * nsq * C * 2)
+        if (!net->conv3_wino) NA(net->act2, (size_t)B * nsq * C * 2)
         NA(net->act3, (size_t)B * o2 * o2 * C * 2) NA(net->act4, (size_t)B * o4 * o4 * C * 2)
         NA(net->f1, (size_t)B * 1024 * 2) NA(net->f2, (size_t)B * 512 * 2)
         if (net->trace_slots) {
@@ -1084,6 +1419,10 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
             NA(net->table2, (size_t)(N_PATTERNS + 1) * 9 * C * 2) NA(net->w2perm, kc * 2)
             NA(net->zero_bias, 9ull * C * 4) NA(net->d_npat, 16)
         }
+        if (net->conv3_wino) {
+            NA(net->v3, 4ull * B * ((n - 2) / 2) * n * C * 2) NA(net->u3, 4ull * C * 3 * C * 2)
+            OZ_CUDA(cudaMemsetAsync(net->v3, 0, 4ull * B * ((n - 2) / 2) * n * C * 2, st));
+        }
 #undef NA
 #define SL(li, ...) if ((rc = setup_layer(net, net->layer[li], net->w[li], net->bias[li], B, __VA_ARGS__))) return rc;
         SL(0, net->act1, C, n, n, n, n, 3, 1, C, 256, EPI_RELU_BF16, net->act2, C)
@@ -1093,6 +1432,28 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         SL(4, net->f1, 1024, 1, 1, 1, 1, 1, 0, 512, 256, EPI_RELU_BF16, net->f2, 512)
         SL(5, net->f2, 512, 1, 1, 1, 1, 1, 0, 128, 128, EPI_HEADS, nullptr, 64)
 #undef SL
+        if (net->conv3_wino) {
+            WinoParams& wp = net->wp;
+            memset(&wp, 0, sizeof(wp));
+            const int T = o2 / 2;
+            wp.chunks_per_tap = C / BLOCK_K;
+            wp.num_kb_eta = 3 * wp.chunks_per_tap;
+            wp.rows_per_board = T * o2;
+            wp.nb = BLOCK_M / wp.rows_per_board;
+            wp.rows_valid = wp.nb * wp.rows_per_board;
+            wp.OW = o2; wp.OH = o2;
+            wp.n_tiles = C / WINO_N;
+            wp.C = C;
+            wp.bmax = B;
+            wp.max_count = B;
+            wp.a_bytes = (unsigned)(wp.rows_valid * BLOCK_K * 2);
+            wp.bias = net->bias[1];
+            wp.out = net->act3;
+            // V as (C, x = n, ty = T, eta*Bmax + board): the box for tap kx is (64 channels, OW, T, nb) at x = kx
+            if ((rc = make_map_A(&net->mapV, net->v3, C, n, T, 4 * B, o2, T, wp.nb))) return rc;
+            if ((rc = make_map_B(&net->mapU, net->u3, 3 * C, 4 * C, WINO_N / 2))) return rc;
+            OZ_CUDA(cudaFuncSetAttribute(oz_wino_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WinoSmem::DYN_BYTES));
+        }
         if (net->conv2_table) {
             // table2 = table1 [19683 x C] x W2perm^T [C x 9C]: one "fc" launch of the GEMM kernel with a linear epilogue
             if ((rc = setup_layer(net, net->tbl, net->w2perm, net->zero_bias, N_PATTERNS, net->table1, C, 1, 1, 1, 1, 1, 0,
@@ -1145,6 +1506,11 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         fold_weights_kernel<<<dim3((K + 31) / 32, (C + 31) / 32), tb, 0, st>>>(w, b, g, be, mu, va, eps, K, C, net->w[li], net->bias[li]);
         OZ_CUDA(cudaGetLastError());
         e->launches++;
+        if (li == 1 && net->conv3_wino) {
+            wino_weights_kernel<<<net->sm_count * 8, 256, 0, st>>>(w, g, va, eps, C, net->u3);
+            OZ_CUDA(cudaGetLastError());
+            e->launches++;
+        }
     }
     if (net->conv2_table) {  // table2[pat][t][:] = W2'[t] . table1[pat]  (93 GFLOP at C=512, once per weight load)
         permute_conv2_weights_kernel<<<net->sm_count * 8, 256, 0, st>>>(net->w[0], C, net->w2perm);
@@ -1223,7 +1589,13 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         int blocks = max_count < net->sm_count * 2 ? max_count : net->sm_count * 2;  // 2 resident CTAs/SM, grid-stride
         const bf16* t2 = net->table2; const float* b2 = net->bias[0];
         unsigned long long* ts = trace_slot(net, "gather");
-#define OZ_T2(NJ) conv2_table_gather_kernel<NJ><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, net->act2, ts)
+#define OZ_T2(NJ)                                                                                                      \
+    if (net->conv3_wino)                                                                                               \
+        conv2_table_gather_kernel<NJ, true><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, \
+                                                                    b2, net->v3, net->Bmax, ts);                      \
+    else                                                                                                               \
+        conv2_table_gather_kernel<NJ, false><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, \
+                                                                     b2, net->act2, net->Bmax, ts)
         switch (C / 256) {
             case 0: case 1: OZ_T2(1); break;
             case 2: OZ_T2(2); break;
@@ -1255,7 +1627,20 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         cfg.attrs = attr;
         cfg.numAttrs = net->pdl ? 1 : 0;
         cudaError_t lerr;
-        if (Lr.use_2sm) {
+        if (li == 1 && net->conv3_wino) {
+            WinoParams wp = net->wp;
+            wp.count = count_dev;
+            wp.max_count = max_count;
+            wp.trace = p.trace;
+            const int m_tiles = (max_count + wp.nb - 1) / wp.nb;
+            const int pairs = ((m_tiles + 1) / 2) * wp.n_tiles;
+            int g2 = 2 * pairs < (net->sm_count & ~1) ? 2 * pairs : (net->sm_count & ~1);
+            if (g2 < 2) g2 = 2;
+            cfg.blockDim = dim3(WINO_THREADS);
+            cfg.gridDim = dim3(g2);
+            cfg.dynamicSmemBytes = WinoSmem::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_wino_kernel, net->mapV, net->mapU, wp);
+        } else if (Lr.use_2sm) {
             int m_tiles = (max_count * p.tile_num + p.tile_den - 1) / p.tile_den;
             int pairs = ((m_tiles + 1) / 2) * p.n_tiles;
             int g2 = 2 * pairs < (net->sm_count & ~1) ? 2 * pairs : (net->sm_count & ~1);
@@ -1313,6 +1698,10 @@ int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes) {
     OZ_REQUIRE(layer >= 0 && layer < 6, "layer %d out of range", layer);
     if (layer == 0 && net->conv2_table) {
         oz_set_error("conv1's output is not materialised while conv2 runs as the table gather (OZ_NET_CONV2=gemm keeps it)");
+        return OZ_ERR_STATE;
+    }
+    if (layer == 1 && net->conv3_wino) {
+        oz_set_error("conv2's output is not materialised while conv3 runs as the Winograd kernel (the default OZ_NET_CONV3=direct keeps it)");
         return OZ_ERR_STATE;
     }
     OZ_REQUIRE(bytes >= 0 && bytes <= sizes[layer] * 2, "bytes out of range");

@@ -22,11 +22,13 @@ def _positions(n, count, seed):
     return np.array(own, dtype=np.uint64), np.array(opp, dtype=np.uint64)
 
 
-@pytest.fixture(params=["table", "gemm"])
+@pytest.fixture(params=["table", "table-wino", "gemm"])
 def conv2_mode(request, monkeypatch):
-    """conv2 runs either as the conv1∘conv2 partial-product table gather (default) or as the tcgen05 implicit GEMM;
-    the mode is read from OZ_NET_CONV2 when an engine is created."""
-    monkeypatch.setenv("OZ_NET_CONV2", request.param)
+    """conv2 runs either as the conv1∘conv2 partial-product table gather (default) or as the tcgen05 implicit GEMM, and
+    with the table conv3 runs either as the direct implicit GEMM (default) or as the opt-in 1-D Winograd F(2,3) SM-pair kernel;
+    the modes are read from OZ_NET_CONV2 / OZ_NET_CONV3 when an engine is created."""
+    monkeypatch.setenv("OZ_NET_CONV2", "gemm" if request.param == "gemm" else "table")
+    monkeypatch.setenv("OZ_NET_CONV3", "wino" if request.param == "table-wino" else "direct")
     return request.param
 
 
@@ -45,10 +47,11 @@ def _check(n, C, B, max_games, seed, randomize_bn=True, conv2_mode="table"):
     # layer-by-layer first: localises a failure
     rows = [n * n, n * n, (n - 2) ** 2, (n - 4) ** 2, 1, 1]
     chans = [C, C, C, C, 1024, 512]
-    if conv2_mode == "table":
+    first = {"table": 1, "table-wino": 2, "gemm": 0}[conv2_mode]
+    for li in range(first):
         with pytest.raises(RuntimeError):
-            e.activation(0, B, rows[0], chans[0])   # conv1's output is never materialised in this mode
-    for li in range(1 if conv2_mode == "table" else 0, 6):
+            e.activation(li, B, rows[li], chans[li])   # conv1's (and, with Winograd conv3, conv2's) output is never materialised
+    for li in range(first, 6):
         got = e.activation(li, B, rows[li], chans[li])
         ref = hidden[li]
         scale = max(1.0, float(np.abs(ref).max()))
@@ -91,6 +94,7 @@ def test_conv2_table_vs_gemm_agree(monkeypatch):
     blob = net.init_weights(n, C, seed=21, randomize_bn=True)
     own, opp = _positions(n, 150, 21)
     outs = []
+    monkeypatch.setenv("OZ_NET_CONV3", "direct")   # keeps conv2's output materialised
     for mode in ("table", "gemm"):
         monkeypatch.setenv("OZ_NET_CONV2", mode)
         e = engine.Engine(n, max_games=256, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
@@ -102,6 +106,29 @@ def test_conv2_table_vs_gemm_agree(monkeypatch):
     scale = max(1.0, float(np.abs(outs[1][2]).max()))
     assert np.abs(outs[0][2] - outs[1][2]).max() <= 0.02 * scale
     assert np.abs(outs[0][0] - outs[1][0]).max() <= TOL and np.abs(outs[0][1] - outs[1][1]).max() <= TOL
+
+
+def test_conv3_wino_vs_direct_agree(monkeypatch):
+    """conv3 as 1-D Winograd F(2,3) (transformed bf16 inputs/filters, fp32 accumulate) against the direct implicit GEMM:
+    same layer output up to bf16 rounding of the transforms, same logits/value within the north-star tolerance."""
+    from othellozero_b200 import engine, net
+    for n, B in ((8, 150), (6, 77)):
+        C = 512
+        blob = net.init_weights(n, C, seed=22, randomize_bn=True)
+        own, opp = _positions(n, B, 22)
+        outs = []
+        for mode in ("wino", "direct"):
+            monkeypatch.setenv("OZ_NET_CONV2", "table")
+            monkeypatch.setenv("OZ_NET_CONV3", mode)
+            e = engine.Engine(n, max_games=256, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+            e.load_weights(blob, C)
+            pi, lg, v = e.net_forward(own, opp)
+            a3 = e.activation(2, B, (n - 2) ** 2, C)
+            outs.append((lg, v, a3))
+            e.close()
+        scale = max(1.0, float(np.abs(outs[1][2]).max()))
+        assert np.abs(outs[0][2] - outs[1][2]).max() <= 0.02 * scale
+        assert np.abs(outs[0][0] - outs[1][0]).max() <= TOL and np.abs(outs[0][1] - outs[1][1]).max() <= TOL
 
 
 def test_net_is_row_independent(conv2_mode):
