@@ -7,6 +7,8 @@
 //
 // All three are integer-ALU bound: a position is 16 bytes in and 8-32 bytes out; the per-ply work is
 // ~470 64-bit logical ops.  Coalesced 8-byte loads/stores, grid sized to fill 148 SMs.
+#include <string.h>
+
 #include "oz_engine.cuh"
 
 using namespace ozbb;
@@ -150,16 +152,52 @@ extern "C" int oz_perft_playouts_dev(int32_t board_size, uint64_t seed, uint64_t
 }
 
 // ---- host-buffer entry points (copies inside) ---------------------------------------------------------
+// The reference calls the rules one position at a time from Python (Othello/__init__.py), so these calls are latency
+// bound: each calling thread keeps ONE device scratch + ONE pinned staging buffer + ONE stream (grown on demand, reused
+// across calls) instead of cudaMalloc/cudaFree per call; inputs go up in one async copy, outputs come back in one.
 namespace {
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-        if (e != cudaSuccess) { oz_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return OZ_ERR_NOMEM; }
+struct HostScratch {
+    int device = -1;
+    unsigned char* dev = nullptr;
+    unsigned char* pin = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+    void release() {
+        if (dev) cudaFree(dev);
+        if (pin) cudaFreeHost(pin);
+        if (st) cudaStreamDestroy(st);
+        dev = pin = nullptr; st = nullptr; cap = 0; device = -1;
+    }
+    ~HostScratch() { release(); }  // at thread exit; errors after runtime teardown are ignored
+    int reserve(int dev_id, size_t bytes) {
+        cudaError_t e = cudaSetDevice(dev_id);
+        if (e != cudaSuccess) { oz_set_error("cudaSetDevice(%d) failed: %s", dev_id, cudaGetErrorString(e)); return OZ_ERR_CUDA; }
+        if (device != dev_id) release();
+        if (!st) {
+            e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            if (e != cudaSuccess) { oz_set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return OZ_ERR_CUDA; }
+            device = dev_id;
+        }
+        if (bytes <= cap) return OZ_OK;
+        size_t want = cap ? cap : 4096;
+        while (want < bytes) want *= 2;
+        if (dev) cudaFree(dev);
+        if (pin) cudaFreeHost(pin);
+        dev = pin = nullptr; cap = 0;
+        e = cudaMalloc((void**)&dev, want);
+        if (e == cudaSuccess) e = cudaMallocHost((void**)&pin, want);
+        if (e != cudaSuccess) {
+            oz_set_error("scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            if (dev) cudaFree(dev);
+            dev = nullptr;
+            return OZ_ERR_NOMEM;
+        }
+        cap = want;
         return OZ_OK;
     }
 };
+thread_local HostScratch g_scratch;
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
 extern "C" int oz_rules_legal_moves_host(int32_t device, int32_t board_size, const uint64_t* own,
@@ -167,15 +205,19 @@ extern "C" int oz_rules_legal_moves_host(int32_t device, int32_t board_size, con
     if (check_board_size(board_size)) return OZ_ERR_INVALID;
     OZ_REQUIRE(n >= 0 && (n == 0 || (own && opp && moves)), "null buffer");
     if (n == 0) return OZ_OK;
-    OZ_CUDA(cudaSetDevice(device));
-    DevBuf a, b, c;
-    size_t bytes = (size_t)n * 8;
-    if (a.alloc(bytes) || b.alloc(bytes) || c.alloc(bytes)) return OZ_ERR_NOMEM;
-    OZ_CUDA(cudaMemcpy(a.p, own, bytes, cudaMemcpyHostToDevice));
-    OZ_CUDA(cudaMemcpy(b.p, opp, bytes, cudaMemcpyHostToDevice));
-    int rc = oz_rules_legal_moves_dev(board_size, (const uint64_t*)a.p, (const uint64_t*)b.p, (uint64_t*)c.p, n, nullptr);
+    HostScratch& S = g_scratch;
+    const size_t b8 = up256((size_t)n * 8);
+    int rc = S.reserve(device, 3 * b8);
     if (rc) return rc;
-    OZ_CUDA(cudaMemcpy(moves, c.p, bytes, cudaMemcpyDeviceToHost));
+    memcpy(S.pin, own, (size_t)n * 8);
+    memcpy(S.pin + b8, opp, (size_t)n * 8);
+    OZ_CUDA(cudaMemcpyAsync(S.dev, S.pin, 2 * b8, cudaMemcpyHostToDevice, S.st));
+    rc = oz_rules_legal_moves_dev(board_size, (const uint64_t*)S.dev, (const uint64_t*)(S.dev + b8),
+                                  (uint64_t*)(S.dev + 2 * b8), n, S.st);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(S.pin + 2 * b8, S.dev + 2 * b8, (size_t)n * 8, cudaMemcpyDeviceToHost, S.st));
+    OZ_CUDA(cudaStreamSynchronize(S.st));
+    memcpy(moves, S.pin + 2 * b8, (size_t)n * 8);
     return OZ_OK;
 }
 
@@ -185,21 +227,27 @@ extern "C" int oz_rules_apply_host(int32_t device, int32_t board_size, const uin
     if (check_board_size(board_size)) return OZ_ERR_INVALID;
     OZ_REQUIRE(n >= 0 && (n == 0 || (own && opp && sq && own_out && opp_out && flags)), "null buffer");
     if (n == 0) return OZ_OK;
-    OZ_CUDA(cudaSetDevice(device));
-    DevBuf a, b, s, oa, ob, f, nl;
-    size_t b8 = (size_t)n * 8, b4 = (size_t)n * 4;
-    if (a.alloc(b8) || b.alloc(b8) || s.alloc(b4) || oa.alloc(b8) || ob.alloc(b8) || f.alloc(b4) || nl.alloc(b8))
-        return OZ_ERR_NOMEM;
-    OZ_CUDA(cudaMemcpy(a.p, own, b8, cudaMemcpyHostToDevice));
-    OZ_CUDA(cudaMemcpy(b.p, opp, b8, cudaMemcpyHostToDevice));
-    OZ_CUDA(cudaMemcpy(s.p, sq, b4, cudaMemcpyHostToDevice));
-    int rc = oz_rules_apply_dev(board_size, (const uint64_t*)a.p, (const uint64_t*)b.p, (const int32_t*)s.p,
-                                (uint64_t*)oa.p, (uint64_t*)ob.p, (uint32_t*)f.p, (uint64_t*)nl.p, n, nullptr);
+    HostScratch& S = g_scratch;
+    const size_t b8 = up256((size_t)n * 8), b4 = up256((size_t)n * 4);
+    // layout: [own | opp | sq] inputs, [own' | opp' | next_legal | flags] outputs
+    const size_t o_in = 0, o_out = 2 * b8 + b4, total = o_out + 3 * b8 + b4;
+    int rc = S.reserve(device, total);
     if (rc) return rc;
-    OZ_CUDA(cudaMemcpy(own_out, oa.p, b8, cudaMemcpyDeviceToHost));
-    OZ_CUDA(cudaMemcpy(opp_out, ob.p, b8, cudaMemcpyDeviceToHost));
-    OZ_CUDA(cudaMemcpy(flags, f.p, b4, cudaMemcpyDeviceToHost));
-    if (next_legal) OZ_CUDA(cudaMemcpy(next_legal, nl.p, b8, cudaMemcpyDeviceToHost));
+    memcpy(S.pin, own, (size_t)n * 8);
+    memcpy(S.pin + b8, opp, (size_t)n * 8);
+    memcpy(S.pin + 2 * b8, sq, (size_t)n * 4);
+    OZ_CUDA(cudaMemcpyAsync(S.dev + o_in, S.pin + o_in, o_out, cudaMemcpyHostToDevice, S.st));
+    unsigned char* d = S.dev;
+    rc = oz_rules_apply_dev(board_size, (const uint64_t*)d, (const uint64_t*)(d + b8), (const int32_t*)(d + 2 * b8),
+                            (uint64_t*)(d + o_out), (uint64_t*)(d + o_out + b8), (uint32_t*)(d + o_out + 3 * b8),
+                            (uint64_t*)(d + o_out + 2 * b8), n, S.st);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(S.pin + o_out, S.dev + o_out, 3 * b8 + b4, cudaMemcpyDeviceToHost, S.st));
+    OZ_CUDA(cudaStreamSynchronize(S.st));
+    memcpy(own_out, S.pin + o_out, (size_t)n * 8);
+    memcpy(opp_out, S.pin + o_out + b8, (size_t)n * 8);
+    if (next_legal) memcpy(next_legal, S.pin + o_out + 2 * b8, (size_t)n * 8);
+    memcpy(flags, S.pin + o_out + 3 * b8, (size_t)n * 4);
     return OZ_OK;
 }
 
@@ -207,16 +255,20 @@ extern "C" int oz_rules_score_host(int32_t device, const uint64_t* black, const 
                                    int32_t* white_points, int64_t n) {
     OZ_REQUIRE(n >= 0 && (n == 0 || (black && white && black_points && white_points)), "null buffer");
     if (n == 0) return OZ_OK;
-    OZ_CUDA(cudaSetDevice(device));
-    DevBuf a, b, ca, cb;
-    size_t b8 = (size_t)n * 8, b4 = (size_t)n * 4;
-    if (a.alloc(b8) || b.alloc(b8) || ca.alloc(b4) || cb.alloc(b4)) return OZ_ERR_NOMEM;
-    OZ_CUDA(cudaMemcpy(a.p, black, b8, cudaMemcpyHostToDevice));
-    OZ_CUDA(cudaMemcpy(b.p, white, b8, cudaMemcpyHostToDevice));
-    int rc = oz_rules_score_dev((const uint64_t*)a.p, (const uint64_t*)b.p, (int32_t*)ca.p, (int32_t*)cb.p, n, nullptr);
+    HostScratch& S = g_scratch;
+    const size_t b8 = up256((size_t)n * 8), b4 = up256((size_t)n * 4);
+    int rc = S.reserve(device, 2 * b8 + 2 * b4);
     if (rc) return rc;
-    OZ_CUDA(cudaMemcpy(black_points, ca.p, b4, cudaMemcpyDeviceToHost));
-    OZ_CUDA(cudaMemcpy(white_points, cb.p, b4, cudaMemcpyDeviceToHost));
+    memcpy(S.pin, black, (size_t)n * 8);
+    memcpy(S.pin + b8, white, (size_t)n * 8);
+    OZ_CUDA(cudaMemcpyAsync(S.dev, S.pin, 2 * b8, cudaMemcpyHostToDevice, S.st));
+    rc = oz_rules_score_dev((const uint64_t*)S.dev, (const uint64_t*)(S.dev + b8), (int32_t*)(S.dev + 2 * b8),
+                            (int32_t*)(S.dev + 2 * b8 + b4), n, S.st);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(S.pin + 2 * b8, S.dev + 2 * b8, 2 * b4, cudaMemcpyDeviceToHost, S.st));
+    OZ_CUDA(cudaStreamSynchronize(S.st));
+    memcpy(black_points, S.pin + 2 * b8, (size_t)n * 4);
+    memcpy(white_points, S.pin + 2 * b8 + b4, (size_t)n * 4);
     return OZ_OK;
 }
 
@@ -226,17 +278,20 @@ extern "C" int oz_perft_playouts_host(int32_t device, int32_t board_size, uint64
     if (check_board_size(board_size)) return OZ_ERR_INVALID;
     OZ_REQUIRE(n_games >= 0 && (n_games == 0 || (black && white && info)), "null buffer");
     if (n_games == 0) return OZ_OK;
-    OZ_CUDA(cudaSetDevice(device));
-    DevBuf b, w, i, m;
-    size_t b8 = (size_t)n_games * 8, b4 = (size_t)n_games * 4;
-    if (b.alloc(b8) || w.alloc(b8) || i.alloc(b4)) return OZ_ERR_NOMEM;
-    if (moves && m.alloc((size_t)n_games * 64)) return OZ_ERR_NOMEM;
-    int rc = oz_perft_playouts_dev(board_size, seed, first_game_id, n_games, max_moves, (uint64_t*)b.p,
-                                   (uint64_t*)w.p, (uint32_t*)i.p, moves ? (uint8_t*)m.p : nullptr, nullptr);
+    HostScratch& S = g_scratch;
+    const size_t b8 = up256((size_t)n_games * 8), b4 = up256((size_t)n_games * 4);
+    const size_t bm = moves ? up256((size_t)n_games * 64) : 0;
+    int rc = S.reserve(device, 2 * b8 + b4 + bm);
     if (rc) return rc;
-    OZ_CUDA(cudaMemcpy(black, b.p, b8, cudaMemcpyDeviceToHost));
-    OZ_CUDA(cudaMemcpy(white, w.p, b8, cudaMemcpyDeviceToHost));
-    OZ_CUDA(cudaMemcpy(info, i.p, b4, cudaMemcpyDeviceToHost));
-    if (moves) OZ_CUDA(cudaMemcpy(moves, m.p, (size_t)n_games * 64, cudaMemcpyDeviceToHost));
+    unsigned char* d = S.dev;
+    rc = oz_perft_playouts_dev(board_size, seed, first_game_id, n_games, max_moves, (uint64_t*)d, (uint64_t*)(d + b8),
+                               (uint32_t*)(d + 2 * b8), moves ? (uint8_t*)(d + 2 * b8 + b4) : nullptr, S.st);
+    if (rc) return rc;
+    OZ_CUDA(cudaMemcpyAsync(S.pin, S.dev, 2 * b8 + b4 + bm, cudaMemcpyDeviceToHost, S.st));
+    OZ_CUDA(cudaStreamSynchronize(S.st));
+    memcpy(black, S.pin, (size_t)n_games * 8);
+    memcpy(white, S.pin + b8, (size_t)n_games * 8);
+    memcpy(info, S.pin + 2 * b8, (size_t)n_games * 4);
+    if (moves) memcpy(moves, S.pin + 2 * b8 + b4, (size_t)n_games * 64);
     return OZ_OK;
 }
