@@ -209,6 +209,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
     n, C, sims, G = 8, args.channels, args.sims, args.games
+    if args.e2e_games <= 0:
+        args.e2e_games = 2 * G
     STEPS_PER_MOVE = (sims + max(1, args.vl) - 1) // max(1, args.vl)
 
     def barrier():
@@ -299,8 +301,11 @@ def run_ours(args):
         # clears it), so nothing evaluated during the timed region above can be reused here
         if mode == E.PRIOR_NET:
             eng.load_weights_from_tensor(wt, C)
-        sb, sw, sp = synthetic_starts(E, G, args.seed + 1, (1 << 24) + first_id, local)
-        ids = np.arange((1 << 24) + first_id, (1 << 24) + first_id + G, dtype=np.uint64)
+        # e2e_games may exceed the G slots: the engine queues the rest and refills slots as episodes end
+        NE = args.e2e_games
+        e_first = (1 << 24) + rank * NE
+        sb, sw, sp = synthetic_starts(E, NE, args.seed + 1, e_first, local)
+        ids = np.arange(e_first, e_first + NE, dtype=np.uint64)
         barrier()
         t0 = time.perf_counter()
         eng.selfplay_begin(args.e2e_games, sims, 1.0, 0.9, args.e2e_moves, sb[:args.e2e_games], sw[:args.e2e_games],
@@ -324,7 +329,9 @@ def run_ours(args):
             e_games, e_moves = float(te[2]), float(te[3])
         e2e = {"value": e_sims / dt, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "games_per_s": e_games / dt, "games": int(e_games), "mean_plies": e_moves / max(1.0, args.e2e_games * world),
-               "seconds": dt, "what": f"{args.e2e_games} games/GPU from host start positions to host example records"
+               "seconds": dt, "slots": int(min(G, args.e2e_games)),
+               "what": f"{args.e2e_games} games/GPU through {min(G, args.e2e_games)} slots (finished slots take the next queued game), "
+                       "from host start positions to host example records"
                                       + ("" if args.e2e_moves < 0 else f", first {args.e2e_moves} moves")}
     gathered = None
     if world > 1:
@@ -586,7 +593,8 @@ def main():
     ap.add_argument("--sims", type=int, default=100)
     ap.add_argument("--channels", type=int, default=512)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--e2e-games", type=int, default=4096)
+    ap.add_argument("--e2e-games", type=int, default=0,
+                    help="complete games per GPU for the e2e figure (default 2 x --games: every slot plays two episodes)")
     ap.add_argument("--e2e-moves", type=int, default=-1)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -149,7 +149,11 @@ int oz_engine_counters(oz_engine* e, uint64_t* out8);
 /* Starts n_games episodes (start positions as oz_search_reset).  temperature > 0: the greedy action is the
  * first arg-max of the visit counts (training.py:48-53); with probability 1-e_greedy a uniformly random legal
  * action from the engine RNG is played instead (training.py:55-56; CPython's RNG stream is not reproduced).
- * max_moves < 0: play to the end. */
+ * max_moves < 0: play to the end.
+ * n_games may exceed max_games (a game QUEUE): the first max_games episodes start at once and a slot whose episode ends
+ * takes the next queued game (fresh tree, its own RNG stream keyed by its game id, default id = game index), so the leaf
+ * batch stays full over the whole job; start arrays then hold n_games entries.  Every game's result is independent of
+ * the slot it ran in and of the other games (tests/test_gpu_search.py::test_game_queue_matches_separate_batches). */
 int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* black, const uint64_t* white,
                       const int32_t* player, const uint64_t* game_ids, int32_t num_sims, double temperature,
                       double e_greedy, int32_t max_moves);

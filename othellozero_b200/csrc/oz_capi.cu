@@ -101,6 +101,8 @@ extern "C" int oz_engine_destroy(oz_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     oz_net_destroy(e);
     for (int i = 0; i < e->n_allocs; ++i) cudaFree(e->allocs[i]);
+    if (e->rec_buf) cudaFree(e->rec_buf);
+    if (e->q_buf) cudaFree(e->q_buf);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -320,17 +322,52 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
     OZ_REQUIRE(temperature > 0.0, "device self-play needs temperature > 0 (T=0 draws random.choice, othelo_mcts.py:54-62)");
     OZ_REQUIRE(e_greedy >= 0.0 && e_greedy <= 1.0, "e_greedy must be in [0,1]");
     if (e->cfg.prior_mode == OZ_PRIOR_HOST) { oz_set_error("self-play needs OZ_PRIOR_HASH or OZ_PRIOR_NET"); return OZ_ERR_STATE; }
+    OZ_REQUIRE(n_games >= 1, "n_games must be >= 1 (got %d)", n_games);
     OZ_CUDA(cudaSetDevice(e->cfg.device));
-    int rc = oz_tree_reset(e, n_games, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
+    // more games than slots: the first max_games start now, the rest are queued and start as slots free up
+    const int slots = n_games < e->cfg.max_games ? n_games : e->cfg.max_games;
+    int rc = oz_tree_reserve_records(e, (size_t)n_games);
+    if (rc) return rc;
+    rc = oz_tree_reset(e, slots, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
     if (rc) return rc;
     OzTreeParams& P = e->tp;
+    if (e->q_buf) { OZ_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(e->q_buf); e->q_buf = nullptr; }
+    P.q_black = P.q_white = nullptr; P.q_player = nullptr; P.q_ids = nullptr;
+    if (n_games > slots && (black || player || game_ids)) {
+        const size_t g8 = ((size_t)n_games * 8 + 255) & ~(size_t)255, g4 = ((size_t)n_games * 4 + 255) & ~(size_t)255;
+        unsigned char* q = nullptr;
+        cudaError_t qerr = cudaMalloc((void**)&q, 3 * g8 + g4);
+        if (qerr != cudaSuccess) { oz_set_error("cudaMalloc for %d queued games failed: %s", n_games, cudaGetErrorString(qerr)); return OZ_ERR_NOMEM; }
+        e->q_buf = q;
+        if (black) {
+            OZ_CUDA(cudaMemcpyAsync(q, black, (size_t)n_games * 8, cudaMemcpyHostToDevice, e->stream));
+            OZ_CUDA(cudaMemcpyAsync(q + g8, white, (size_t)n_games * 8, cudaMemcpyHostToDevice, e->stream));
+            P.q_black = (const u64*)q; P.q_white = (const u64*)(q + g8);
+        }
+        if (game_ids) {
+            OZ_CUDA(cudaMemcpyAsync(q + 2 * g8, game_ids, (size_t)n_games * 8, cudaMemcpyHostToDevice, e->stream));
+            P.q_ids = (const u64*)(q + 2 * g8);
+        }
+        if (player) {
+            OZ_CUDA(cudaMemcpyAsync(q + 3 * g8, player, (size_t)n_games * 4, cudaMemcpyHostToDevice, e->stream));
+            P.q_player = (const int*)(q + 3 * g8);
+        }
+    }
+    P.total_games = n_games;
+    e->rec_games = n_games;
     P.selfplay = 1;
     P.num_sims = num_sims;
     P.max_moves = max_moves;
     P.e_greedy = e_greedy;
-    e->h_pinned[1] = n_games;
+    e->h_pinned[1] = slots;
+    e->h_pinned[5] = slots;  // next queued game
     OZ_CUDA(cudaMemcpyAsync(P.n_active, &e->h_pinned[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(P.next_game, &e->h_pinned[5], sizeof(int), cudaMemcpyHostToDevice, e->stream));
     OZ_CUDA(cudaMemsetAsync(P.rec_action, 0xFF, (size_t)n_games * 64, e->stream));
+    if (n_games > slots) {
+        OZ_CUDA(cudaMemsetAsync(P.winner + slots, 0xFF, (size_t)(n_games - slots) * 4, e->stream));
+        OZ_CUDA(cudaMemsetAsync(P.rec_nmoves + slots, 0, (size_t)(n_games - slots) * 4, e->stream));
+    }
     search_begin_kernel<<<(P.G + 255) / 256, 256, 0, e->stream>>>(P, num_sims);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
@@ -383,16 +420,16 @@ extern "C" int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active) {
 extern "C" int oz_selfplay_get_records(oz_engine* e, uint64_t* rec_black, uint64_t* rec_white, uint8_t* rec_action,
                                        uint8_t* rec_player, int32_t* n_moves, int32_t* winner, int32_t* rec_visits) {
     OZ_REQUIRE(e && rec_black && rec_white && rec_action && rec_player && n_moves && winner, "null argument");
-    OZ_REQUIRE(e->n_games > 0, "no games");
+    OZ_REQUIRE(e->n_games > 0 && e->rec_games > 0, "no games");
     OZ_REQUIRE(!rec_visits || e->cfg.log_visits, "engine was created without log_visits");
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     OzTreeParams& P = e->tp;
-    size_t g = (size_t)e->n_games;
+    size_t g = (size_t)e->rec_games;  // every game of the job, queued ones included
     OZ_CUDA(cudaMemcpyAsync(rec_black, P.rec_black, g * 64 * 8, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(rec_white, P.rec_white, g * 64 * 8, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(rec_action, P.rec_action, g * 64, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(rec_player, P.rec_player, g * 64, cudaMemcpyDeviceToHost, e->stream));
-    OZ_CUDA(cudaMemcpyAsync(n_moves, P.ply, g * 4, cudaMemcpyDeviceToHost, e->stream));
+    OZ_CUDA(cudaMemcpyAsync(n_moves, P.rec_nmoves, g * 4, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(winner, P.winner, g * 4, cudaMemcpyDeviceToHost, e->stream));
     if (rec_visits) OZ_CUDA(cudaMemcpyAsync(rec_visits, P.rec_visits, g * 64 * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaStreamSynchronize(e->stream));

@@ -83,6 +83,13 @@ struct OzTreeParams {
     // self-play
     int num_sims; int max_moves; double e_greedy; u64 seed;
     u64* rec_black; u64* rec_white; unsigned char* rec_action; unsigned char* rec_player; int* rec_visits;
+    int* rec_nmoves;  // [record capacity] plies played so far, by game index
+    // game queue: a slot whose episode ends starts game *next_game (while < total_games) - self-play keeps the leaf batch
+    // full over a job of more games than slots.  Records / winner / rec_nmoves are indexed by GAME (slot_game[slot]).
+    int total_games;
+    int* next_game;
+    int* slot_game;                                          // [G]
+    const u64* q_black; const u64* q_white; const int* q_player; const u64* q_ids;  // [total_games] start positions or null
     // counters (device)
     u64* counters;  // see oz_engine_counters
     int* n_active;
@@ -102,6 +109,10 @@ struct oz_engine {
     u64 launches = 0;
     size_t cache_entries = 0;
     int max_leaves = 0;        // max_games * vl_width: capacity of the leaf batch and of the network
+    int rec_games = 0;         // games whose records the last oz_selfplay_begin covers (>= n_games slots with a queue)
+    size_t rec_capacity = 0;   // games the record buffers hold (grown on demand, see oz_tree_reserve_records)
+    void* rec_buf = nullptr;   // one allocation behind tp.rec_* / tp.winner / tp.rec_nmoves
+    void* q_buf = nullptr;     // queued start positions of the current self-play job
     // device allocations (freed in destroy)
     void* allocs[64];
     int n_allocs = 0;
@@ -118,6 +129,7 @@ int oz_tree_alloc(oz_engine* e);
 int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white, const int* player, const u64* ids,
                   bool clear);
 int oz_tree_step(oz_engine* e);  // one tree kernel launch
+int oz_tree_reserve_records(oz_engine* e, size_t games);
 int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev);
 int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev);
 int oz_tree_hash_eval(oz_engine* e);      // wave mode + closed-form priors: evaluate the parked leaves

@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
     u64* table = P.table + ((size_t)slot << P.table_log2);
     const int n = P.n;
     int sims_left = P.sims_left[slot];
+    int gi = P.slot_game[slot];  // game index: where this episode's records go
     u64 c_sims = 0, c_nodes = 0, c_term = 0, c_trans = 0, c_moves = 0, c_hits = 0, c_alias = 0;
     int c_depth = 0;
     SimPath path{0, 0, 0, 0};
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             if (!(coin <= P.e_greedy)) aj = (int)pick_index(sm64(base + 2ull * (u64)ply + 1ull), (u32)k);
             int sq = kth_set_bit(legal, aj);
             if (ply < 64) {
-                size_t ri = (size_t)slot * 64 + ply;
+                size_t ri = (size_t)gi * 64 + ply;
                 if (lane == 0) {
                     P.rec_black[ri] = black; P.rec_white[ri] = white;
                     P.rec_action[ri] = (unsigned char)sq; P.rec_player[ri] = (unsigned char)player;
@@ -454,23 +455,40 @@ __global__ void __launch_bounds__(TREE_WARPS * 32) tree_step_kernel(const OzTree
             black = player ? opp : own;
             white = player ? own : opp;
             ++ply; ++c_moves;
-            if (fl & MOVE_FINISHED) {
-                status = OZ_GAME_FINISHED;
-                if (lane == 0) {
-                    P.winner[slot] = (popc(black) >= popc(white)) ? 0 : 1;
-                    atomicSub(P.n_active, 1);
+            if (lane == 0) P.rec_nmoves[gi] = ply;
+            const bool over = (fl & MOVE_FINISHED) != 0;
+            if (over || (P.max_moves >= 0 && ply >= P.max_moves)) {
+                if (lane == 0) P.winner[gi] = over ? ((popc(black) >= popc(white)) ? 0 : 1) : -1;
+                // the episode is over: take the next queued game into this slot, or retire the slot
+                int ng = P.total_games;
+                if (lane == 0) ng = atomicAdd(P.next_game, 1);
+                ng = __shfl_sync(FULLW, ng, 0);
+                if (ng >= P.total_games) {
+                    status = OZ_GAME_FINISHED;
+                    if (lane == 0) atomicSub(P.n_active, 1);
+                    break;
                 }
-                break;
+                gi = ng;
+                if (P.q_black) { black = P.q_black[ng]; white = P.q_white[ng]; }
+                else initial_position(n, &black, &white);
+                player = P.q_player ? P.q_player[ng] : 0;
+                ply = 0;
+                uint4* t4 = reinterpret_cast<uint4*>(table);  // a fresh tree: empty table, empty pool (training.py:30-32)
+                for (int i = lane; i < (1 << (P.table_log2 - 1)); i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                if (lane == 0) {
+                    P.slot_game[slot] = ng;
+                    P.game_id[slot] = P.q_ids ? P.q_ids[ng] : (u64)ng;
+                    P.bump[slot] = 1;
+                    P.root_node[slot] = -1;
+                }
+                __syncwarp();
+                sims_left = P.num_sims;
+                continue;
             }
             u32 ins;
             int nr = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
             if (lane == 0) P.root_node[slot] = nr;
             __syncwarp();
-            if (P.max_moves >= 0 && ply >= P.max_moves) {
-                status = OZ_GAME_FINISHED;
-                if (lane == 0) { P.winner[slot] = -1; atomicSub(P.n_active, 1); }
-                break;
-            }
             sims_left = P.num_sims;
             continue;
         }
@@ -764,16 +782,17 @@ int oz_tree_alloc(oz_engine* e) {
     int rc = 0;
 #define A(field, T, count) if ((rc = oz_dev_alloc<T>(e, (T**)&P.field, (size_t)(count)))) return rc;
     A(black, u64, G) A(white, u64, G) A(player, int, G) A(status, int, G) A(root_node, int, G)
-    A(sims_left, int, G) A(ply, int, G) A(game_id, u64, G) A(winner, int, G)
+    A(sims_left, int, G) A(ply, int, G) A(game_id, u64, G) A(slot_game, int, G)
     A(pend_own, u64, GV) A(pend_opp, u64, GV) A(pend_legal, u64, GV) A(pend_parent, int, GV) A(pend_edge, int, GV)
     A(pend_depth, int, GV) A(pend_leaf, int, GV) A(pend_count, int, G)
     A(path_node, u32, GV * OZ_MAX_DEPTH) A(path_edge, u32, GV * OZ_MAX_DEPTH)
     A(arena, unsigned char, (size_t)G * stride) A(bump, u32, G) A(table, u64, (size_t)G << log2)
     A(leaf_own, u64, GV) A(leaf_opp, u64, GV) A(leaf_count, int, 4)
-    A(rec_black, u64, (size_t)G * 64) A(rec_white, u64, (size_t)G * 64) A(rec_action, unsigned char, (size_t)G * 64)
-    A(rec_player, unsigned char, (size_t)G * 64)
     A(counters, u64, 8) A(n_active, int, 4)
-    if (e->cfg.log_visits) { A(rec_visits, int, (size_t)G * 64 * 64) } else { P.rec_visits = nullptr; }
+    P.next_game = P.n_active + 1;
+    P.total_games = 0;
+    P.q_black = P.q_white = nullptr; P.q_player = nullptr; P.q_ids = nullptr;
+    if ((rc = oz_tree_reserve_records(e, (size_t)G))) return rc;
     P.cache_tags = nullptr; P.cache_log2_buckets = 0;
     if (e->cfg.eval_cache_log2 > 0 && e->cfg.prior_mode == OZ_PRIOR_NET) {
         int lg = e->cfg.eval_cache_log2;
@@ -800,6 +819,32 @@ int oz_tree_alloc(oz_engine* e) {
     return OZ_OK;
 }
 
+// Per-game record buffers (positions, actions, movers, visit counts, winner, plies): one allocation, regrown when a
+// self-play job queues more games than the buffers hold.
+int oz_tree_reserve_records(oz_engine* e, size_t games) {
+    OzTreeParams& P = e->tp;
+    if (games <= e->rec_capacity) return OZ_OK;
+    if (e->rec_buf) { cudaStreamSynchronize(e->stream); cudaFree(e->rec_buf); e->rec_buf = nullptr; e->rec_capacity = 0; }
+    const size_t per_game = 64 * 8 * 2 + 64 * 2 + 4 * 2 + (e->cfg.log_visits ? 64 * 64 * 4 : 0);
+    unsigned char* q = nullptr;
+    cudaError_t err = cudaMalloc((void**)&q, games * per_game + 256);
+    if (err != cudaSuccess) {
+        oz_set_error("cudaMalloc(%zu bytes) for %zu game records failed: %s", games * per_game, games, cudaGetErrorString(err));
+        return OZ_ERR_NOMEM;
+    }
+    e->rec_buf = q;
+    e->rec_capacity = games;
+    P.rec_black = (u64*)q; q += games * 64 * 8;
+    P.rec_white = (u64*)q; q += games * 64 * 8;
+    P.rec_visits = nullptr;
+    if (e->cfg.log_visits) { P.rec_visits = (int*)q; q += games * 64 * 64 * 4; }
+    P.winner = (int*)q; q += games * 4;
+    P.rec_nmoves = (int*)q; q += games * 4;
+    P.rec_action = q; q += games * 64;
+    P.rec_player = q;
+    return OZ_OK;
+}
+
 __global__ void tree_init_slots_kernel(const OzTreeParams P, int n_games, const u64* __restrict__ black,
                                        const u64* __restrict__ white, const int* __restrict__ player,
                                        const u64* __restrict__ ids, int clear) {
@@ -816,6 +861,8 @@ __global__ void tree_init_slots_kernel(const OzTreeParams P, int n_games, const 
             P.bump[g] = 1;  // offset 0 is never a node, so (off+1) != 0 and child >= 0 stays unambiguous
             P.ply[g] = 0;
             P.winner[g] = -1;
+            P.rec_nmoves[g] = 0;
+            P.slot_game[g] = g;
         }
         P.status[g] = OZ_GAME_IDLE;
         P.pend_count[g] = 0;

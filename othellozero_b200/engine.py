@@ -88,7 +88,7 @@ class Engine:
         h = C.c_void_p()
         check(self._L.oz_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
-        self.n_games = 0
+        self.n_games = self.n_slots = 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -106,7 +106,7 @@ class Engine:
         black, white, player, game_ids = _u64(black), _u64(white), _i32(player), _u64(game_ids)
         check(self._L.oz_search_reset(self._h, n_games, ptr(black, u64p), ptr(white, u64p), ptr(player, i32p),
                                       ptr(game_ids, u64p)))
-        self.n_games = n_games
+        self.n_games = self.n_slots = n_games
 
     def set_roots(self, black, white, player=None):
         black, white, player = _u64(black), _u64(white), _i32(player)
@@ -132,8 +132,8 @@ class Engine:
 
     def visits(self):
         """-> (visits [n_games, 64] by square bit r*8+c, ns [n_games])"""
-        v = np.zeros((self.n_games, 64), dtype=np.int32)
-        ns = np.zeros(self.n_games, dtype=np.int32)
+        v = np.zeros((self.n_slots, 64), dtype=np.int32)
+        ns = np.zeros(self.n_slots, dtype=np.int32)
         check(self._L.oz_search_get_visits(self._h, ptr(v, i32p), ptr(ns, i32p)))
         return v, ns
 
@@ -145,7 +145,7 @@ class Engine:
         return q, p, tag
 
     def status(self):
-        s = np.zeros(self.n_games, dtype=np.int32)
+        s = np.zeros(self.n_slots, dtype=np.int32)
         check(self._L.oz_search_get_status(self._h, ptr(s, i32p)))
         return s
 
@@ -166,11 +166,17 @@ class Engine:
     # -- self-play ---------------------------------------------------------------------------------
     def selfplay_begin(self, n_games: int, num_sims: int, temperature: float = 1.0, e_greedy: float = 1.0,
                        max_moves: int = -1, black=None, white=None, player=None, game_ids=None):
+        """n_games may exceed max_games: the first max_games episodes start at once, the others are queued and a slot
+        whose episode ends starts the next one (records cover all n_games, indexed by game)."""
         black, white, player, game_ids = _u64(black), _u64(white), _i32(player), _u64(game_ids)
+        for a in (black, white, player, game_ids):
+            assert a is None or a.size >= n_games, "start arrays must cover every game"
+
         check(self._L.oz_selfplay_begin(self._h, n_games, ptr(black, u64p), ptr(white, u64p), ptr(player, i32p),
                                         ptr(game_ids, u64p), num_sims, float(temperature), float(e_greedy),
                                         max_moves))
         self.n_games = n_games
+        self.n_slots = min(n_games, self.max_games)
 
     def selfplay_run(self, steps: int = -1) -> int:
         na = C.c_int32(0)
@@ -191,7 +197,7 @@ class Engine:
         return dict(black=rb, white=rw, action=ra, player=rp, n_moves=nm, winner=win, visits=rv)
 
     def positions(self):
-        g = self.n_games
+        g = self.n_slots
         b = np.zeros(g, dtype=np.uint64)
         w = np.zeros(g, dtype=np.uint64)
         p = np.zeros(g, dtype=np.int32)

@@ -107,9 +107,11 @@ def records_to_examples(rec: dict, game: int, board_size: int, reference_aliasin
 
 
 def execute_episodes(n_episodes, board_size, neural_network, degree_exploration, num_simulations, policy_temperature,
-                     e_greedy, device: int = 0, seed: int = 0, reference_aliasing: bool = False, game_ids=None):
-    """n_episodes x training.execute_episode as one GPU batch; returns a list of example lists."""
-    sp = SelfPlay(board_size, neural_network, degree_exploration, max_games=n_episodes,
+                     e_greedy, device: int = 0, seed: int = 0, reference_aliasing: bool = False, game_ids=None,
+                     max_concurrent: int = 4096):
+    """n_episodes x training.execute_episode as one GPU job; returns a list of example lists.  At most `max_concurrent`
+    episodes are in flight (node pools are per slot); the others are queued on the device and start as slots free up."""
+    sp = SelfPlay(board_size, neural_network, degree_exploration, max_games=min(n_episodes, max_concurrent),
                   num_simulations=num_simulations, device=device, seed=seed)
     try:
         rec = sp.play(n_episodes, policy_temperature, e_greedy, game_ids=game_ids)

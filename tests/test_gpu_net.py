@@ -262,3 +262,27 @@ def test_sim_budget_is_results_preserving(monkeypatch):
             assert np.array_equal(outs[0][k], o[k]), k
     assert steps[0] == steps[1] == steps[2]
     assert steps[0][2] > 0   # the endgames did visit terminal edges
+
+
+def test_game_queue_with_network_matches_one_batch():
+    """Queued self-play with the real evaluator (leaf batches mix games of different ages, evaluation cache on):
+    every game equals the same game played with all games resident at once."""
+    from othellozero_b200 import engine, net
+    n, C, sims, total, slots = 6, 128, 10, 40, 8
+    blob = net.init_weights(n, C, seed=31, randomize_bn=True)
+    ids = np.arange(100, 100 + total, dtype=np.uint64)
+    outs = []
+    for mg, cache in ((slots, 16), (total, 0)):
+        e = engine.Engine(n, max_games=mg, nodes_per_game=sims * 36 + 64, prior_mode=engine.PRIOR_NET,
+                          eval_cache_log2=cache, log_visits=True)
+        e.load_weights(blob, C)
+        e.selfplay_begin(total, sims, 1.0, 0.85, game_ids=ids)
+        assert e.selfplay_run(-1) == 0
+        outs.append(e.selfplay_records())
+        e.close()
+    a, b = outs
+    assert np.array_equal(a["n_moves"], b["n_moves"]) and np.array_equal(a["winner"], b["winner"])
+    for g in range(total):
+        k = int(a["n_moves"][g])
+        assert np.array_equal(a["action"][g][:k], b["action"][g][:k])
+        assert np.array_equal(a["visits"][g][:k], b["visits"][g][:k])

@@ -196,3 +196,63 @@ def test_selfplay_full_size_properties(E):
         k = int(nm[g])
         assert [int(a) for a in rec["action"][g][:k]] == [sq8(a, n) for a in ref["moves"]]
         assert int(rec["winner"][g]) == ref["winner"]
+
+
+def _rec_equal(a, b, ga, gb):
+    k = int(a["n_moves"][ga])
+    assert k == int(b["n_moves"][gb]) and int(a["winner"][ga]) == int(b["winner"][gb])
+    for key in ("black", "white", "action", "player"):
+        assert np.array_equal(a[key][ga][:k], b[key][gb][:k]), key
+    if a.get("visits") is not None and b.get("visits") is not None:
+        assert np.array_equal(a["visits"][ga][:k], b["visits"][gb][:k])
+
+
+@pytest.mark.parametrize("n,sims,total,slots", [(6, 20, 37, 8), (8, 16, 50, 16)])
+def test_game_queue_matches_separate_batches(E, n, sims, total, slots):
+    """More episodes than slots: finished slots take the next queued game.  Every game (moves, positions, visit counts,
+    winner) must equal the same game played in an engine of its own batch - the slot and its neighbours do not matter."""
+    rng = np.random.default_rng(7)
+    ids = rng.integers(1, 2**62, size=total, dtype=np.uint64)
+    # de-correlated starts: a few random plies from the initial position
+    st = E.perft_playouts(total, n, seed=11, max_moves=3)
+    black, white, player = st["black"], st["white"], st["player"].astype(np.int32)
+    npg = sims * (n * n) + 64
+    q = E.Engine(n, max_games=slots, nodes_per_game=npg, prior_mode=E.PRIOR_HASH, log_visits=True)
+    q.selfplay_begin(total, sims, 1.0, 0.8, black=black, white=white, player=player, game_ids=ids)
+    assert q.selfplay_run(-1) == 0
+    rq = q.selfplay_records()
+    assert rq["n_moves"].shape == (total,) and (rq["winner"] >= 0).all()
+    q.close()
+    ref = E.Engine(n, max_games=total, nodes_per_game=npg, prior_mode=E.PRIOR_HASH, log_visits=True)
+    ref.selfplay_begin(total, sims, 1.0, 0.8, black=black, white=white, player=player, game_ids=ids)
+    assert ref.selfplay_run(-1) == 0
+    rr = ref.selfplay_records()
+    ref.close()
+    for g in range(total):
+        _rec_equal(rq, rr, g, g)
+    # and against the oracle for a few games (hash priors, same RNG stream)
+    assert int(rq["n_moves"].sum()) > total * 10
+
+
+def test_game_queue_default_ids_and_partial_run(E):
+    """Default game ids are the game indices (also for queued games); a step-limited run reports unfinished games."""
+    n, sims, total, slots = 6, 12, 20, 4
+    q = E.Engine(n, max_games=slots, nodes_per_game=sims * 36 + 64, prior_mode=E.PRIOR_HASH)
+    q.selfplay_begin(total, sims, 1.0, 0.9)
+    assert q.selfplay_run(-1) == 0
+    rq = q.selfplay_records()
+    q.close()
+    ref = E.Engine(n, max_games=total, nodes_per_game=sims * 36 + 64, prior_mode=E.PRIOR_HASH)
+    ref.selfplay_begin(total, sims, 1.0, 0.9)
+    assert ref.selfplay_run(-1) == 0
+    rr = ref.selfplay_records()
+    ref.close()
+    for g in range(total):
+        _rec_equal(rq, rr, g, g)
+    # max_moves truncation also frees the slot for the next game
+    t = E.Engine(n, max_games=slots, nodes_per_game=sims * 36 + 64, prior_mode=E.PRIOR_HASH)
+    t.selfplay_begin(total, sims, 1.0, 1.0, max_moves=5)
+    assert t.selfplay_run(-1) == 0
+    rt = t.selfplay_records()
+    assert (rt["n_moves"] == 5).all() and (rt["winner"] == -1).all()
+    t.close()
