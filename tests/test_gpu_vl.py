@@ -112,3 +112,23 @@ def test_wave_selfplay_with_net_and_cache(E):
         e.close()
     for k in ("action", "n_moves", "winner", "visits"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_wave_mode_game_queue_matches_one_batch(E):
+    """Queued self-play in wave mode: a game's moves and visit counts do not depend on the slot it ran in."""
+    n, sims, V, total, slots = 6, 24, 4, 21, 5
+    ids = np.arange(500, 500 + total, dtype=np.uint64)
+    outs = []
+    for mg in (slots, total):
+        e = E.Engine(n, max_games=mg, nodes_per_game=sims * 36 + 64, prior_mode=E.PRIOR_HASH, vl_width=V,
+                     log_visits=True)
+        e.selfplay_begin(total, sims, 1.0, 0.85, game_ids=ids)
+        assert e.selfplay_run(-1) == 0
+        outs.append(e.selfplay_records())
+        e.close()
+    a, b = outs
+    assert np.array_equal(a["n_moves"], b["n_moves"]) and np.array_equal(a["winner"], b["winner"])
+    for g in range(total):
+        k = int(a["n_moves"][g])
+        assert np.array_equal(a["action"][g][:k], b["action"][g][:k])
+        assert np.array_equal(a["visits"][g][:k], b["visits"][g][:k])
