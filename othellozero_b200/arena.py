@@ -3,8 +3,11 @@
 * ``OthelloAgent`` / ``RandomOthelloAgent`` / ``NeuralNetworkOthelloAgent`` / ``duel_between_agents`` mirror the
   reference game by game (same names, same semantics: the network agent always plays at temperature 0 with
   ``random.choice`` over the arg-max set, agents.py:44-68, othelo_mcts.py:54-62).
-* ``pit`` plays many network-vs-network games at once: two engines (each agent keeps its own tree for the whole
-  game, agents.py:49), one search launch per move for all games whose turn it is.
+* ``pit`` plays many games at once, network vs network or network vs the random agent: one engine per network side
+  (each agent keeps its own tree for the whole game, agents.py:49), one search launch per move for all games whose
+  turn it is.
+* ``duels_between_neural_networks`` / ``evaluate_neural_network`` are the batched forms of the worker work types
+  (workers.py:18-21); ``selfplay.B200Worker`` dispatches all three work types.
 
 The reference's own drivers ``training.duel_between_neural_networks`` / ``evaluate_neural_network`` are broken
 (SURVEY §0.8); ``pit`` follows the working semantics of main.py:165-197 (who won, counted per game).
@@ -68,23 +71,37 @@ def duel_between_agents(game, agent_1, agent_2):
     return players_agents[winner], points
 
 
+RANDOM_AGENT = "random"   # a side of pit() that plays RandomOthelloAgent's policy (agents.py:20-24)
+
+
 def _mode_for(net):
     if isinstance(net, HashPriorNet):
         return _e.PRIOR_HASH
     if isinstance(net, B200NNet):
         return _e.PRIOR_NET
-    raise TypeError("pit() needs B200NNet or HashPriorNet agents")
+    raise TypeError("pit() needs B200NNet / HashPriorNet agents (or RANDOM_AGENT)")
+
+
+def _kth_set_bit(mask: int, k: int) -> int:
+    for _ in range(k):
+        mask &= mask - 1
+    return (mask & -mask).bit_length() - 1
 
 
 def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1, n_games=64, device=0, rng=None,
         start_black=None, start_white=None, start_player=None):
     """n_games simultaneous duels, net_black playing BLACK.  Returns dict(winner [n_games] 0/1, black, white, plies).
-    Ties in the visit counts are broken with ``rng.choice`` (default: Python's ``random``) like the reference."""
+    Ties in the visit counts are broken with ``rng.choice`` (default: Python's ``random``) like the reference.
+    Either side may be ``RANDOM_AGENT``: it plays ``rng.choice`` over its legal moves in row-major order
+    (RandomOthelloAgent, agents.py:20-24; main.py:165-197 evaluates the network against it)."""
     rng = rng or random
     n = board_size
     nodes = num_simulations * (n * n) + 64
     engines = []
     for net in (net_black, net_white):
+        if isinstance(net, str) and net == RANDOM_AGENT:
+            engines.append(None)
+            continue
         mode = _mode_for(net)
         e = _e.Engine(n, max_games=n_games, nodes_per_game=nodes, prior_mode=mode, c_puct=float(degree_exploration),
                       device=device)
@@ -103,7 +120,8 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
         white = np.array(start_white, dtype=np.uint64)
         player = np.array(start_player, dtype=np.int32)
     for e in engines:
-        e.reset(n_games, black, white, player)
+        if e is not None:
+            e.reset(n_games, black, white, player)
     finished = np.zeros(n_games, dtype=bool)
     plies = np.zeros(n_games, dtype=np.int32)
     try:
@@ -112,19 +130,28 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
                 turn = (~finished) & (player == side)
                 if not turn.any():
                     continue
-                # games where it is not this agent's turn get a root with no legal move for the mover: the kernel
-                # skips them (0 simulations), exactly like an agent that is not asked to play
-                rb = np.where(turn, black, 0).astype(np.uint64)
-                rw = np.where(turn, white, 0).astype(np.uint64)
-                e.set_roots(rb, rw, player)
-                e.search(num_simulations)
-                visits, _ = e.visits()
                 idx = np.nonzero(turn)[0]
-                sq = np.zeros(idx.size, dtype=np.int32)
-                for j, g in enumerate(idx):
-                    v = visits[g]
-                    bests = np.nonzero(v == v.max())[0]
-                    sq[j] = int(bests[0]) if bests.size == 1 else int(rng.choice(list(bests)))
+                if e is None:  # the random agent: uniform over the legal moves (GPU move generator, host RNG)
+                    own = np.where(player[idx] == 0, black[idx], white[idx])
+                    opp = np.where(player[idx] == 0, white[idx], black[idx])
+                    legal = _e.legal_moves(own, opp, n, device)
+                    sq = np.zeros(idx.size, dtype=np.int32)
+                    for j, m in enumerate(legal):
+                        m = int(m)
+                        sq[j] = _kth_set_bit(m, rng.choice(range(bin(m).count("1"))))
+                else:
+                    # games where it is not this agent's turn get a root with no legal move for the mover: the
+                    # kernel skips them (0 simulations), exactly like an agent that is not asked to play
+                    rb = np.where(turn, black, 0).astype(np.uint64)
+                    rw = np.where(turn, white, 0).astype(np.uint64)
+                    e.set_roots(rb, rw, player)
+                    e.search(num_simulations)
+                    visits, _ = e.visits()
+                    sq = np.zeros(idx.size, dtype=np.int32)
+                    for j, g in enumerate(idx):
+                        v = visits[g]
+                        bests = np.nonzero(v == v.max())[0]
+                        sq[j] = int(bests[0]) if bests.size == 1 else int(rng.choice(list(bests)))
                 own = np.where(player[idx] == 0, black[idx], white[idx])
                 opp = np.where(player[idx] == 0, white[idx], black[idx])
                 o2, p2, fl, _ = _e.apply_moves(own, opp, sq, n, device)
@@ -138,6 +165,39 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
                 finished[idx] = (fl & 4) != 0
     finally:
         for e in engines:
-            e.close()
+            if e is not None:
+                e.close()
     cb, cw = _e.score(black, white, device)
     return dict(winner=np.where(cb >= cw, 0, 1), black=black, white=white, plies=plies, points=np.maximum(cb, cw))
+
+
+# ---- batched arena drivers (the worker work types of workers.py:18-21,72-79) -----------------------------------------
+def duels_between_neural_networks(n_duels, board_size, neural_network_1, neural_network_2, degree_exploration,
+                                  num_simulations, device=0, rng=None):
+    """``n_duels`` x training.duel_between_neural_networks (training.py:75-89) as one batch: network 1 plays BLACK
+    (agent_1 of duel_between_agents, agents.py:71-74); each entry is 0 if network 1 won, else 1."""
+    out = pit(board_size, neural_network_1, neural_network_2, num_simulations, degree_exploration, n_games=n_duels,
+              device=device, rng=rng)
+    return [int(w) for w in out["winner"]]
+
+
+def evaluate_neural_network(board_size, total_iterations, neural_network, num_simulations, degree_exploration,
+                            agent_class=RandomOthelloAgent, agent_arguments=(), device=0, rng=None, repeats=1):
+    """training.evaluate_neural_network (training.py:92-115) with the working semantics of main.py:165-197: the network
+    meets ``agent_class`` (RandomOthelloAgent) in ``total_iterations`` games, colours shuffled per game; returns the
+    network's wins.  ``repeats`` > 1 plays that many evaluations in the same batch and returns a list of win counts."""
+    if agent_class is not RandomOthelloAgent:
+        raise TypeError("the batched evaluation plays against RandomOthelloAgent (main.py:165-197)")
+    rng = rng or random
+    games = total_iterations * repeats
+    net_is_black = np.array([rng.random() < 0.5 for _ in range(games)], dtype=bool)   # random.shuffle of two agents
+    net_won = np.zeros(games, dtype=bool)
+    for black_side in (True, False):
+        sel = np.nonzero(net_is_black == black_side)[0]
+        if sel.size == 0:
+            continue
+        a, b = (neural_network, RANDOM_AGENT) if black_side else (RANDOM_AGENT, neural_network)
+        out = pit(board_size, a, b, num_simulations, degree_exploration, n_games=int(sel.size), device=device, rng=rng)
+        net_won[sel] = out["winner"] == (0 if black_side else 1)
+    wins = net_won.reshape(repeats, total_iterations).sum(axis=1)
+    return int(wins[0]) if repeats == 1 else [int(w) for w in wins]

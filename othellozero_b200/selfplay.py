@@ -173,14 +173,34 @@ def make_b200_worker(worker_base=Worker, device: int = 0, seed: int = 0):
         def _run(self, work_type, iterations, args, kwargs):
             # workers.py:57-65 runs the target once per iteration; here all iterations are one GPU batch and
             # _results still receives one entry per iteration (workers.py:54-55,180-184).
-            if work_type != WorkType.EXECUTE_EPISODE:
-                raise TypeError('B200Worker implements WorkType.EXECUTE_EPISODE; arena work types are "next" rows')
-            logging.info(f'Task {work_type}: {iterations} episodes as one GPU batch on cuda:{self.device}')
-            results = execute_episodes(iterations, *args, device=self.device, seed=self.seed, **kwargs)
+            # (the reference compares work types with `is`, workers.py:72-79; equal strings from another module's
+            # WorkType class must match too, hence ==)
+            if work_type == WorkType.EXECUTE_EPISODE:
+                logging.info(f'Task {work_type}: {iterations} episodes as one GPU job on cuda:{self.device}')
+                results = execute_episodes(iterations, *args, device=self.device, seed=self.seed, **kwargs)
+            elif work_type == WorkType.DUEL_BETWEEN_NEURAL_NETWORKS:
+                from . import arena
+                logging.info(f'Task {work_type}: {iterations} duels as one GPU batch on cuda:{self.device}')
+                results = arena.duels_between_neural_networks(iterations, *args, device=self.device, **kwargs)
+            elif work_type == WorkType.EVALUATE_NEURAL_NETWORK:
+                from . import arena
+                logging.info(f'Task {work_type}: {iterations} evaluations as one GPU batch on cuda:{self.device}')
+                results = arena.evaluate_neural_network(*args, device=self.device, repeats=iterations, **kwargs)
+                results = results if isinstance(results, list) else [results]
+            else:
+                raise TypeError('expecting WorkType object')
             self._results.extend(results)
 
         def execute_episode(self, *args, **kwargs):
             return execute_episode(*args, device=self.device, seed=self.seed, **kwargs)
+
+        def duel_between_neural_networks(self, *args, **kwargs):
+            from . import arena
+            return arena.duels_between_neural_networks(1, *args, device=self.device, **kwargs)[0]
+
+        def evaluate_neural_network(self, *args, **kwargs):
+            from . import arena
+            return arena.evaluate_neural_network(*args, device=self.device, **kwargs)
 
     return B200Worker
 

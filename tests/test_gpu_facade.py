@@ -177,3 +177,78 @@ def test_agents_mirror_duel(monkeypatch):
     g2 = OthelloGame(n)
     w2, _ = duel_between_agents(g2, RandomOthelloAgent(g2), RandomOthelloAgent(g2))
     assert g2.has_finished()
+
+
+class _FirstChoiceRng(_FirstChoice):
+    """rng for pit(): first element of every choice; colour coin flips alternate."""
+    def __init__(self):
+        self.k = 0
+
+    def random(self):
+        self.k += 1
+        return 0.25 if self.k % 2 else 0.75
+
+
+def _oracle_duel_vs_first_move(n, sims, net_is_black):
+    """A NeuralNetworkOthelloAgent (T=0, first arg-max) against an agent that always plays its first legal move in
+    row-major order (RandomOthelloAgent with random.choice -> seq[0]), restated with the oracle."""
+    tree = oracle.Mcts(n, 1.0)
+    board, player, plies = oracle.initial_board(n), 0, 0
+    while not oracle.has_finished(board):
+        if (player == 0) == net_is_black:
+            for _ in range(sims):
+                tree.simulate(board, player)
+            canon = board if player == 0 else board[..., ::-1]
+            _, v = tree.visits(np.ascontiguousarray(canon))
+            a = int(np.argmax(v.ravel()))
+        else:
+            r, c = oracle.valid_actions(board, player)[0]
+            a = int(r) * n + int(c)
+        board = oracle.flip_board(board, player, a // n, a % n)
+        plies += 1
+        nxt = 1 - player
+        if not oracle.valid_actions(board, nxt):
+            nxt = player
+        player = nxt
+    return oracle.winner(board), oracle.board_to_bits(board), plies
+
+
+@pytest.mark.parametrize("net_is_black", [True, False])
+def test_pit_network_vs_random_agent_matches_oracle(net_is_black):
+    from othellozero_b200.arena import RANDOM_AGENT, pit
+    from othellozero_b200.mcts import HashPriorNet
+    n, sims = 6, 16
+    (wch, pts), (fb, fw), plies = _oracle_duel_vs_first_move(n, sims, net_is_black)
+    sides = (HashPriorNet(), RANDOM_AGENT) if net_is_black else (RANDOM_AGENT, HashPriorNet())
+    out = pit(n, sides[0], sides[1], sims, 1, n_games=2, rng=_FirstChoice)
+    assert out["winner"].tolist() == [wch] * 2 and out["plies"].tolist() == [plies] * 2
+    assert [int(x) for x in out["black"]] == [fb] * 2 and [int(x) for x in out["white"]] == [fw] * 2
+
+
+def test_batched_arena_drivers_and_worker_work_types():
+    """workers.py:18-21,72-79: the three work types through the worker seam, one entry per iteration."""
+    import random
+    from othellozero_b200 import arena
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.selfplay import B200Worker, WorkType
+    n, sims = 6, 12
+    net = HashPriorNet()
+    # evaluate: alternating colours, every random choice = first element -> two distinct deterministic games
+    wins = arena.evaluate_neural_network(n, 6, net, sims, 1, rng=_FirstChoiceRng())
+    (w_b, _), _, _ = _oracle_duel_vs_first_move(n, sims, True)
+    (w_w, _), _, _ = _oracle_duel_vs_first_move(n, sims, False)
+    assert wins == 3 * int(w_b == 0) + 3 * int(w_w == 1)
+    assert arena.evaluate_neural_network(n, 4, net, sims, 1, rng=random.Random(3), repeats=3).__len__() == 3
+    with pytest.raises(TypeError):
+        arena.evaluate_neural_network(n, 2, net, sims, 1, agent_class=arena.NeuralNetworkOthelloAgent)
+    w = B200Worker()
+    w.run(WorkType.DUEL_BETWEEN_NEURAL_NETWORKS, 4, n, net, net, 1, sims)
+    w.wait()
+    duels = w.get_results()
+    assert len(duels) == 4 and set(duels) <= {0, 1}
+    w.run(WorkType.EVALUATE_NEURAL_NETWORK, 2, n, 5, net, sims, 1, arena.RandomOthelloAgent, ())
+    w.wait()
+    ev = w.get_results()
+    assert len(ev) == 2 and all(0 <= x <= 5 for x in ev)
+    with pytest.raises(TypeError):
+        w._run("no such work", 1, (), {})
