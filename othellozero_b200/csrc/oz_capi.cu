@@ -256,14 +256,12 @@ extern "C" int oz_search_put_priors(oz_engine* e, const float* pi, const float* 
     }
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     const int nsq = e->tp.nsq;
-    float* tmp = nullptr;
-    OZ_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n_leaves * nsq * sizeof(float), e->stream));
+    float* tmp = (float*)e->scratch;  // n_leaves <= max_leaves rows of nsq <= 64 floats
     OZ_CUDA(cudaMemcpyAsync(tmp, pi, (size_t)n_leaves * nsq * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     scatter_priors_kernel<<<(n_leaves * nsq + 255) / 256, 256, 0, e->stream>>>(e->leaf_pi, tmp, n_leaves, nsq);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
     OZ_CUDA(cudaMemcpyAsync(e->leaf_v, v, (size_t)n_leaves * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    OZ_CUDA(cudaFreeAsync(tmp, e->stream));
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     e->host_leaves = 0;
     return OZ_OK;
@@ -273,14 +271,12 @@ extern "C" int oz_search_get_visits(oz_engine* e, int32_t* visits, int32_t* ns) 
     OZ_REQUIRE(e && visits && ns, "null argument");
     OZ_REQUIRE(e->n_games > 0, "oz_search_reset first");
     OZ_CUDA(cudaSetDevice(e->cfg.device));
-    int* dv = nullptr;
     size_t nv = (size_t)e->n_games * 64;
-    OZ_CUDA(cudaMallocAsync((void**)&dv, (nv + e->n_games) * sizeof(int), e->stream));
+    int* dv = (int*)e->scratch;
     int rc = oz_tree_visits(e, dv, dv + nv);
     if (rc) return rc;
     OZ_CUDA(cudaMemcpyAsync(visits, dv, nv * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(ns, dv + nv, (size_t)e->n_games * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    OZ_CUDA(cudaFreeAsync(dv, e->stream));
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     return OZ_OK;
 }
@@ -289,8 +285,7 @@ extern "C" int oz_search_get_root_stats(oz_engine* e, int32_t game, double* q, d
     OZ_REQUIRE(e && q && p && qtag, "null argument");
     OZ_REQUIRE(game >= 0 && game < e->n_games, "game %d out of range", game);
     OZ_CUDA(cudaSetDevice(e->cfg.device));
-    double* dq = nullptr;
-    OZ_CUDA(cudaMallocAsync((void**)&dq, 128 * sizeof(double) + 72 * sizeof(int), e->stream));
+    double* dq = (double*)e->scratch;
     int* dt = (int*)(dq + 128);
     int rc = oz_tree_root_stats(e, game, dq, dq + 64, dt);
     if (rc) return rc;
@@ -299,7 +294,6 @@ extern "C" int oz_search_get_root_stats(oz_engine* e, int32_t game, double* q, d
     OZ_CUDA(cudaMemcpyAsync(p, dq + 64, 64 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(qtag, dt, 64 * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     OZ_CUDA(cudaMemcpyAsync(&found, dt + 64, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-    OZ_CUDA(cudaFreeAsync(dq, e->stream));
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     if (found < 0) { oz_set_error("root of game %d is not in the tree", game); return OZ_ERR_STATE; }
     return OZ_OK;

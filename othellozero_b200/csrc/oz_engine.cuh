@@ -113,6 +113,8 @@ struct oz_engine {
     size_t rec_capacity = 0;   // games the record buffers hold (grown on demand, see oz_tree_reserve_records)
     void* rec_buf = nullptr;   // one allocation behind tp.rec_* / tp.winner / tp.rec_nmoves
     void* q_buf = nullptr;     // queued start positions of the current self-play job
+    unsigned char* scratch = nullptr;  // persistent device staging for the host-buffer entry points (no per-call
+    size_t scratch_bytes = 0;          // cudaMallocAsync/FreeAsync: measured 2-350 ms per call when the pool is trimmed)
     // device allocations (freed in destroy)
     void* allocs[64];
     int n_allocs = 0;

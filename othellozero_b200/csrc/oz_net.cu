@@ -1484,7 +1484,7 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
     const float* d = blob;
     float* staged = nullptr;
     if (!on_device) {
-        OZ_CUDA(cudaMallocAsync((void**)&staged, (size_t)need * 4, st));
+        OZ_CUDA(cudaMalloc((void**)&staged, (size_t)need * 4));
         OZ_CUDA(cudaMemcpyAsync(staged, blob, (size_t)need * 4, cudaMemcpyHostToDevice, st));
         d = staged;
     }
@@ -1556,8 +1556,8 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         OZ_CUDA(cudaGetLastError());
         e->launches += 2;
     }
-    if (staged) OZ_CUDA(cudaFreeAsync(staged, st));
     OZ_CUDA(cudaStreamSynchronize(st));
+    if (staged) OZ_CUDA(cudaFree(staged));
     net->loaded = true;
     return OZ_OK;
 }

@@ -806,6 +806,8 @@ int oz_tree_alloc(oz_engine* e) {
         OZ_CUDA(cudaMemsetAsync(P.cache_tags, 0, entries * sizeof(u64), e->stream));
     }
 #undef A
+    e->scratch_bytes = GV * 64 * sizeof(float) + (size_t)G * 66 * sizeof(int) + 4096;  // put_priors / visits / reset staging
+    if ((rc = oz_dev_alloc<unsigned char>(e, &e->scratch, e->scratch_bytes))) return rc;
     if ((rc = oz_dev_alloc<float>(e, &e->leaf_pi, GV * 64))) return rc;
     if ((rc = oz_dev_alloc<float>(e, &e->leaf_logits, GV * 64))) return rc;
     if ((rc = oz_dev_alloc<float>(e, &e->leaf_v, GV))) return rc;
@@ -896,21 +898,20 @@ int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white,
     OZ_REQUIRE((black == nullptr) == (white == nullptr), "black/white must both be given or both NULL");
     u64 *d_b = nullptr, *d_w = nullptr, *d_id = nullptr;
     int* d_p = nullptr;
-    // staging buffers live in the (not yet used) leaf arrays' neighbours: allocate temporaries
-    size_t b8 = (size_t)n_games * 8, b4 = (size_t)n_games * 4;
+    // host start arrays are staged in the engine's persistent scratch: [black | white | ids | player], G entries each
+    const size_t b8 = (size_t)n_games * 8, b4 = (size_t)n_games * 4, g8 = (size_t)G * 8;
     if (black) {
-        OZ_CUDA(cudaMallocAsync((void**)&d_b, b8, e->stream));
-        OZ_CUDA(cudaMallocAsync((void**)&d_w, b8, e->stream));
+        d_b = (u64*)e->scratch; d_w = (u64*)(e->scratch + g8);
         OZ_CUDA(cudaMemcpyAsync(d_b, black, b8, cudaMemcpyHostToDevice, e->stream));
         OZ_CUDA(cudaMemcpyAsync(d_w, white, b8, cudaMemcpyHostToDevice, e->stream));
     }
-    if (player) {
-        OZ_CUDA(cudaMallocAsync((void**)&d_p, b4, e->stream));
-        OZ_CUDA(cudaMemcpyAsync(d_p, player, b4, cudaMemcpyHostToDevice, e->stream));
-    }
     if (ids) {
-        OZ_CUDA(cudaMallocAsync((void**)&d_id, b8, e->stream));
+        d_id = (u64*)(e->scratch + 2 * g8);
         OZ_CUDA(cudaMemcpyAsync(d_id, ids, b8, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (player) {
+        d_p = (int*)(e->scratch + 3 * g8);
+        OZ_CUDA(cudaMemcpyAsync(d_p, player, b4, cudaMemcpyHostToDevice, e->stream));
     }
     if (clear) {
         OZ_CUDA(cudaMemsetAsync(P.table, 0, ((size_t)n_games << P.table_log2) * sizeof(u64), e->stream));
@@ -926,9 +927,6 @@ int oz_tree_reset(oz_engine* e, int n_games, const u64* black, const u64* white,
         OZ_CUDA(cudaGetLastError());
         e->launches++;
     }
-    if (d_b) { cudaFreeAsync(d_b, e->stream); cudaFreeAsync(d_w, e->stream); }
-    if (d_p) cudaFreeAsync(d_p, e->stream);
-    if (d_id) cudaFreeAsync(d_id, e->stream);
     e->n_games = n_games;
     return OZ_OK;
 }
