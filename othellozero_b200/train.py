@@ -113,11 +113,11 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
     history = []
     model.train()
     for ep in range(epochs):
-        perm = torch.randperm(n, generator=gen)  # keras fit shuffles every epoch
-        tot = np.zeros(3)
+        perm = torch.randperm(n, generator=gen).to(device)  # keras fit shuffles every epoch
+        tot = torch.zeros(3, dtype=torch.float64, device=device)  # summed on the device: no host sync per step
         cnt = 0
         for i in range(0, n, batch_size):
-            idx = perm[i:i + batch_size].to(device)
+            idx = perm[i:i + batch_size]
             if idx.numel() < 2:
                 continue  # BatchNorm needs more than one sample
             logits, v = model(xb[idx])
@@ -128,9 +128,9 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
             loss.backward()
             torch.nn.utils.clip_grad_value_(model.parameters(), clipvalue)      # Adam(clipvalue=0.5)
             opt.step()
-            tot += np.array([loss.item(), pi_loss.item(), v_loss.item()]) * idx.numel()
+            tot += torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double() * idx.numel()
             cnt += idx.numel()
-        history.append(tuple(tot / max(1, cnt)))
+        history.append(tuple(float(x) for x in (tot / max(1, cnt)).cpu()))
         if verbose:
             print(f"epoch {ep + 1}/{epochs}: loss {history[-1][0]:.4f} pi {history[-1][1]:.4f} v {history[-1][2]:.4f}")
     model.eval()
