@@ -62,6 +62,79 @@ def pack_blob(weights: dict, board_size: int, channels: int = 512) -> np.ndarray
                            for name, _ in blob_layout(board_size, channels)])
 
 
+# ---- Keras .h5 weight files (Net/NNet.py:89-96: model.save_weights(path, save_format='h5') / load_weights) -------------
+# File layout written by Keras 2.4 (requirements.txt:35): root (or the 'model_weights' group of a full-model file) has the
+# attribute 'layer_names' = every layer of model.layers in order; each layer group has 'weight_names' and one dataset per
+# weight.  Concatenated in that order this is model.get_weights(), i.e. exactly the blob order of blob_layout().
+# The HDF5 container itself is read/written by h5py (not installed in the authoring image, so the import is deferred and
+# the mapping is tested against a stand-in group object, tests/test_h5_mapping_cpu.py).
+KERAS_LAYER_NAMES = [("conv2d", "conv1", "bn1", "batch_normalization"), ("conv2d_1", "conv2", "bn2", "batch_normalization_1"),
+                     ("conv2d_2", "conv3", "bn3", "batch_normalization_2"), ("conv2d_3", "conv4", "bn4", "batch_normalization_3"),
+                     ("dense", "fc1", "bn5", "batch_normalization_4"), ("dense_1", "fc2", "bn6", "batch_normalization_5")]
+
+
+def _txt(x) -> str:
+    return x.decode() if isinstance(x, (bytes, np.bytes_)) else str(x)
+
+
+def blob_from_h5_group(root, board_size: int, channels: int = 512) -> np.ndarray:
+    """`root`: an h5py.File / Group (anything with .attrs, `in` and [] access) holding Keras layer groups."""
+    g = root["model_weights"] if "model_weights" in root else root
+    arrays = []
+    for ln in g.attrs["layer_names"]:
+        grp = g[_txt(ln)]
+        for wn in grp.attrs["weight_names"]:
+            arrays.append(np.asarray(grp[_txt(wn)], dtype=np.float32))
+    layout = blob_layout(board_size, channels)
+    if len(arrays) != len(layout):
+        raise ValueError(f"checkpoint holds {len(arrays)} weight arrays, OthelloNN({board_size}x{board_size}, C={channels}) "
+                         f"has {len(layout)}")
+    for a, (name, shape) in zip(arrays, layout):
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"checkpoint array for {name} has shape {tuple(a.shape)}, expected {tuple(shape)}")
+    return np.concatenate([a.reshape(-1) for a in arrays]).astype(np.float32)
+
+
+def write_h5_group(root, blob: np.ndarray, board_size: int, channels: int = 512):
+    """Fills `root` (h5py.File / Group, or a stand-in with .attrs, create_group, create_dataset) the way Keras does."""
+    w = unpack_blob(np.asarray(blob, dtype=np.float32), board_size, channels)
+    layers = []
+    for lname, key, bnkey, bnname in KERAS_LAYER_NAMES:
+        layers.append((lname, [(f"{lname}/kernel:0", w[f"{key}.kernel"]), (f"{lname}/bias:0", w[f"{key}.bias"])]))
+        layers.append((bnname, [(f"{bnname}/gamma:0", w[f"{bnkey}.gamma"]), (f"{bnname}/beta:0", w[f"{bnkey}.beta"]),
+                                (f"{bnname}/moving_mean:0", w[f"{bnkey}.mean"]),
+                                (f"{bnname}/moving_variance:0", w[f"{bnkey}.var"])]))
+    for head in ("pi", "v"):
+        layers.append((head, [(f"{head}/kernel:0", w[f"{head}.kernel"]), (f"{head}/bias:0", w[f"{head}.bias"])]))
+    root.attrs["layer_names"] = [ln.encode() for ln, _ in layers]
+    root.attrs["backend"] = b"tensorflow"
+    root.attrs["keras_version"] = b"2.4.0"
+    for ln, weights in layers:
+        grp = root.create_group(ln)
+        grp.attrs["weight_names"] = [wn.encode() for wn, _ in weights]
+        for wn, arr in weights:
+            grp.create_dataset(wn, data=np.ascontiguousarray(arr, dtype=np.float32))
+
+
+def _h5py():
+    try:
+        import h5py
+        return h5py
+    except ImportError as e:  # pragma: no cover - h5py is absent in the authoring image
+        raise RuntimeError("Keras .h5 checkpoints need the h5py package (pip install h5py); "
+                           "use a .npz path for the native format") from e
+
+
+def load_keras_h5(filepath, board_size: int, channels: int = 512) -> np.ndarray:
+    with _h5py().File(filepath, "r") as f:
+        return blob_from_h5_group(f, board_size, channels)
+
+
+def save_keras_h5(filepath, blob: np.ndarray, board_size: int, channels: int = 512):
+    with _h5py().File(filepath, "w") as f:
+        write_h5_group(f, blob, board_size, channels)
+
+
 def init_weights(board_size: int, channels: int = 512, seed: int = 0, randomize_bn: bool = False) -> np.ndarray:
     """Keras defaults: glorot-uniform kernels, zero biases, BN gamma=1 beta=0 mean=0 var=1.
     randomize_bn=True perturbs BN statistics / biases so that folding is exercised by the tests."""
@@ -158,9 +231,16 @@ class B200NNet:
         return history
 
     def save_checkpoint(self, filepath):
+        """Net/NNet.py:89-91.  '.h5' paths are written in Keras' save_weights layout (needs h5py); anything else is the
+        native .npz (float32 blob in Keras get_weights() order)."""
+        if str(filepath).endswith(".h5"):
+            return save_keras_h5(filepath, self.blob, self.board_size_x, self.channels)
         np.savez(filepath, blob=self.blob, board_size=self.board_size_x, channels=self.channels)
 
     def load_checkpoint(self, filepath):
+        """Net/NNet.py:93-96 ('.h5' = a Keras save_weights file of the reference's NNetWrapper; needs h5py)."""
+        if str(filepath).endswith(".h5"):
+            return self.set_weights(load_keras_h5(filepath, self.board_size_x, self.channels))
         d = np.load(filepath if str(filepath).endswith(".npz") else str(filepath) + ".npz")
         assert int(d["board_size"]) == self.board_size_x and int(d["channels"]) == self.channels
         self.set_weights(d["blob"])
