@@ -161,12 +161,12 @@ int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* black, cons
  * >= 1 simulation per step).  steps < 0: run until every game has finished.  *n_active = games still running.
  * OZ_PRIOR_HOST is not supported here (use the search API). */
 int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active);
-/* Per-move records, HOST buffers sized [n_games][64] (rec_visits [n_games][64][64], may be NULL unless
- * log_visits): position before the move as black/white bitboards, action square bit, mover; n_moves,
+/* Per-move records of EVERY game of the job (queued ones included, indexed by game), HOST buffers sized [n_games][64]
+ * (rec_visits [n_games][64][64], may be NULL unless log_visits): position before the move as black/white bitboards, action square bit, mover; n_moves,
  * winner (0 BLACK / 1 WHITE, draw -> BLACK, Othello/__init__.py:254-256; -1 unfinished) per game. */
 int oz_selfplay_get_records(oz_engine* e, uint64_t* rec_black, uint64_t* rec_white, uint8_t* rec_action,
                             uint8_t* rec_player, int32_t* n_moves, int32_t* winner, int32_t* rec_visits);
-/* Current positions [n_games] (HOST buffers; any may be NULL). */
+/* Current positions of the min(n_games, max_games) slots (HOST buffers; any may be NULL). */
 int oz_selfplay_get_positions(oz_engine* e, uint64_t* black, uint64_t* white, int32_t* player);
 
 /* ---- network: NNetWrapper.predict / OthelloNN (Net/NNet.py:70-87, Net/OthelloNN.py:42-52) -- */
