@@ -70,12 +70,12 @@ def main():
     new_blob = None
     hist = None
     if rank == 0:
-        rows = allrows[:args.max_examples]
-        examples = []
-        for b, w, meta in rows:
-            a, player, win = int(meta) & 0xFF, (int(meta) >> 8) & 0xFF, (int(meta) >> 16) & 0xFF
-            pol = np.zeros((n, n)); pol[a >> 3][a & 7] = 1
-            examples.append((oznet.bits_to_board(int(b), int(w), n), pol, 1 if win == player else -1))
+        rows = np.asarray(allrows[:args.max_examples])
+        meta = rows[:, 2].astype(np.int64)
+        act, player, win = meta & 0xFF, (meta >> 8) & 0xFF, (meta >> 16) & 0xFF
+        boards = selfplay.bits_to_boards(rows[:, 0], rows[:, 1], n)
+        pols = np.zeros((rows.shape[0], n, n)); pols[np.arange(rows.shape[0]), act >> 3, act & 7] = 1
+        examples = list(zip(boards, pols, np.where(win == player, 1, -1).tolist()))
         new_blob, hist = train.train_blob(old.blob, examples, n, C, epochs=args.epochs, device=f"cuda:{local}")
     sync(); t["train_s"] = time.perf_counter() - t0
     # ---- C1: broadcast the new weights ---------------------------------------------------------------------------
