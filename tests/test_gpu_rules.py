@@ -95,3 +95,39 @@ def test_playouts_full_size_properties(eng):
     # shard independence: games are keyed by global id
     part = eng.perft_playouts(1000, 8, seed=0, first_game_id=500000)
     assert np.array_equal(part["black"], a["black"][500000:501000])
+
+
+def test_host_entry_points_from_many_threads_and_sizes():
+    """The host-buffer rules calls keep one staging buffer per calling thread (grown on demand): concurrent callers with
+    different batch sizes must not see each other's data."""
+    import threading
+    from othellozero_b200 import engine as E
+    n = 8
+    base = E.perft_playouts(3000, n, seed=5, max_moves=11)
+    own = np.where(base["player"] == 0, base["black"], base["white"])
+    opp = np.where(base["player"] == 0, base["white"], base["black"])
+    ref_legal = E.legal_moves(own, opp, n)
+    ref_score = E.score(base["black"], base["white"])
+    errors = []
+
+    def worker(tid):
+        try:
+            rng = np.random.default_rng(tid)
+            for it in range(30):
+                k = int(rng.integers(1, 3000))            # sizes shrink and grow -> the scratch is reused and regrown
+                lo = int(rng.integers(0, 3000 - k + 1))
+                sl = slice(lo, lo + k)
+                assert np.array_equal(E.legal_moves(own[sl], opp[sl], n), ref_legal[sl])
+                cb, cw = E.score(base["black"][sl], base["white"][sl])
+                assert np.array_equal(cb, ref_score[0][sl]) and np.array_equal(cw, ref_score[1][sl])
+                out = E.perft_playouts(k, n, seed=5, first_game_id=lo, max_moves=11)
+                assert np.array_equal(out["black"], base["black"][sl]) and np.array_equal(out["white"], base["white"][sl])
+        except Exception as ex:  # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
