@@ -265,31 +265,41 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer =====
             pdl_wait();  // the activations we are about to read are the previous kernel's output
+            // This one thread feeds the whole pipeline, so its per-stage instruction count is the supply rate: no integer
+            // division in the k loop (taps and chunks are nested counters) and everything tile-invariant hoisted.  The
+            // original `tap = kb / chunks_per_tap; ky = tap / ntaps_x` cost ~700 clk per stage against the 512 clk the
+            // MMAs of a stage take.
             int stage = 0; uint32_t phase = 0;
+            const int ntaps_y = p.num_kb / (p.chunks_per_tap * p.ntaps_x);
+            const uint32_t tx_bytes = p.a_bytes + (unsigned)B_STAGE_BYTES;
+            const uint32_t off_main_after_half = (uint32_t)(p.half_rows * 128);
+            const uint32_t off_half_after_main = (uint32_t)(p.nb * p.rows_per_board * 128);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.n_tiles, n_idx = tile - m_tile * p.n_tiles;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), p.a_bytes + (unsigned)B_STAGE_BYTES);
-                    const int tap = kb / p.chunks_per_tap, chunk = kb - tap * p.chunks_per_tap;
-                    const int ky = tap / p.ntaps_x, kx = tap - ky * p.ntaps_x;
-                    const uint32_t dstA = sA + stage * A_STAGE_BYTES;
-                    if (!p.split) {
-                        tma_load_4d(dstA, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad, m_tile * p.nb);
-                    } else {
-                        const int hb0 = m_tile * p.halves, b0 = hb0 >> 1;
-                        if (hb0 & 1) {  // lower half of board b0, then nb whole boards
-                            tma_load_4d(dstA, &mapA2, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad + p.half_h, b0);
-                            tma_load_4d(dstA + (uint32_t)(p.half_rows * 128), &mapA, full_bar(stage), chunk * BLOCK_K,
-                                        kx - p.pad, ky - p.pad, b0 + 1);
-                        } else {        // nb whole boards, then the upper half of the next one
-                            tma_load_4d(dstA, &mapA, full_bar(stage), chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0);
-                            tma_load_4d(dstA + (uint32_t)(p.nb * p.rows_per_board * 128), &mapA2, full_bar(stage),
-                                        chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0 + p.nb);
+                const int n0 = n_idx * BLOCK_N;
+                // A boxes of this tile: (map, board, y offset, smem offset) x 2; the second is unused without split tiles
+                const int hb0 = m_tile * p.halves;
+                const bool odd = p.split && (hb0 & 1);
+                const int bA = p.split ? ((hb0 >> 1) + (odd ? 1 : 0)) : m_tile * p.nb;      // whole-board box (mapA)
+                const int bH = (hb0 >> 1) + (odd ? 0 : p.nb);                                  // half-board box (mapA2)
+                const uint32_t offA = odd ? off_main_after_half : 0u;
+                const uint32_t offH = odd ? 0u : off_half_after_main;
+                const int yH = odd ? p.half_h : 0;
+                int kcol = 0;
+                for (int ky = -p.pad; ky < ntaps_y - p.pad; ++ky) {
+                    for (int kx = -p.pad; kx < p.ntaps_x - p.pad; ++kx) {
+                        for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
+                            const uint32_t fb = full_bar(stage);
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            mbar_expect_tx(fb, tx_bytes);
+                            const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                            tma_load_4d(dstA + offA, &mapA, fb, c0, kx, ky, bA);
+                            if (p.split) tma_load_4d(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
+                            tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            kcol += BLOCK_K;
+                            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
-                    tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, full_bar(stage), kb * BLOCK_K, n_idx * BLOCK_N);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -525,33 +535,39 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier) =====
             pdl_wait();
+            // division-free k loop, tile-invariant work hoisted: see the producer of oz_gemm_kernel
             int stage = 0; uint32_t phase = 0;
+            const int ntaps_y = p.num_kb / (p.chunks_per_tap * p.ntaps_x);
+            const uint32_t tx_bytes = 2u * (p.a_bytes + (unsigned)B2_STAGE_BYTES);
+            const uint32_t off_main_after_half = (uint32_t)(p.half_rows * 128);
+            const uint32_t off_half_after_main = (uint32_t)(p.nb * p.rows_per_board * 128);
+            const uint32_t fb0 = mapa_cluster(full_bar(0), 0);  // the leader's full[0]; full[s] is 8*s bytes further
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
                 const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
                 const int m_tile = 2 * m_pair + (int)rank;
-                for (int kb = 0; kb < p.num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t fb = mapa_cluster(full_bar(stage), 0);
-                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (p.a_bytes + (unsigned)B2_STAGE_BYTES));
-                    const int tap = kb / p.chunks_per_tap, chunk = kb - tap * p.chunks_per_tap;
-                    const int ky = tap / p.ntaps_x, kx = tap - ky * p.ntaps_x;
-                    const uint32_t dstA = sA + stage * A_STAGE_BYTES;
-                    if (!p.split) {
-                        tma_load_4d_2sm(dstA, &mapA, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad, m_tile * p.nb);
-                    } else {
-                        const int hb0 = m_tile * p.halves, b0 = hb0 >> 1;
-                        if (hb0 & 1) {
-                            tma_load_4d_2sm(dstA, &mapA2, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad + p.half_h, b0);
-                            tma_load_4d_2sm(dstA + (uint32_t)(p.half_rows * 128), &mapA, fb, chunk * BLOCK_K, kx - p.pad,
-                                            ky - p.pad, b0 + 1);
-                        } else {
-                            tma_load_4d_2sm(dstA, &mapA, fb, chunk * BLOCK_K, kx - p.pad, ky - p.pad, b0);
-                            tma_load_4d_2sm(dstA + (uint32_t)(p.nb * p.rows_per_board * 128), &mapA2, fb, chunk * BLOCK_K,
-                                            kx - p.pad, ky - p.pad, b0 + p.nb);
+                const int n0 = n_idx * BLOCK_N + (int)rank * 128;
+                const int hb0 = m_tile * p.halves;
+                const bool odd = p.split && (hb0 & 1);
+                const int bA = p.split ? ((hb0 >> 1) + (odd ? 1 : 0)) : m_tile * p.nb;
+                const int bH = (hb0 >> 1) + (odd ? 0 : p.nb);
+                const uint32_t offA = odd ? off_main_after_half : 0u;
+                const uint32_t offH = odd ? 0u : off_half_after_main;
+                const int yH = odd ? p.half_h : 0;
+                int kcol = 0;
+                for (int ky = -p.pad; ky < ntaps_y - p.pad; ++ky) {
+                    for (int kx = -p.pad; kx < p.ntaps_x - p.pad; ++kx) {
+                        for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t fb = fb0 + 8u * (uint32_t)stage;
+                            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                            const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                            tma_load_4d_2sm(dstA + offA, &mapA, fb, c0, kx, ky, bA);
+                            if (p.split) tma_load_4d_2sm(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
+                            tma_load_2d_2sm(sB + stage * B2_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            kcol += BLOCK_K;
+                            if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                         }
                     }
-                    tma_load_2d_2sm(sB + stage * B2_STAGE_BYTES, &mapB, fb, kb * BLOCK_K, n_idx * BLOCK_N + (int)rank * 128);
-                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -734,17 +750,22 @@ oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
                 const int m_pair = pt / p.n_tiles, n_idx = pt - m_pair * p.n_tiles;
                 const int m_tile = 2 * m_pair + (int)rank;
-                for (int eta = 0; eta < 4; ++eta) {
-                    for (int kb = 0; kb < p.num_kb_eta; ++kb) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t fb = mapa_cluster(full_bar(stage), 0);
-                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (p.a_bytes + (unsigned)WB_STAGE_BYTES));
-                        const int kx = kb / p.chunks_per_tap, chunk = kb - kx * p.chunks_per_tap;
-                        tma_load_4d_2sm(sA + stage * A_STAGE_BYTES, &mapV, fb, chunk * BLOCK_K, kx, 0,
-                                        eta * p.bmax + m_tile * p.nb);
-                        tma_load_2d_2sm(sB + stage * WB_STAGE_BYTES, &mapU, fb, kb * BLOCK_K,
-                                        eta * p.C + n_idx * WINO_N + (int)rank * (WINO_N / 2));
-                        if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
+                const uint32_t tx_bytes = 2u * (p.a_bytes + (unsigned)WB_STAGE_BYTES);
+                const uint32_t fb0 = mapa_cluster(full_bar(0), 0);
+                for (int eta = 0; eta < 4; ++eta) {  // division-free k loop: see the producer of oz_gemm_kernel
+                    const int brow = eta * p.bmax + m_tile * p.nb;
+                    const int urow = eta * p.C + n_idx * WINO_N + (int)rank * (WINO_N / 2);
+                    int kcol = 0;
+                    for (int kx = 0; kx < 3; ++kx) {
+                        for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u);
+                            const uint32_t fb = fb0 + 8u * (uint32_t)stage;
+                            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                            tma_load_4d_2sm(sA + stage * A_STAGE_BYTES, &mapV, fb, c0, kx, 0, brow);
+                            tma_load_2d_2sm(sB + stage * WB_STAGE_BYTES, &mapU, fb, kcol, urow);
+                            kcol += BLOCK_K;
+                            if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
+                        }
                     }
                 }
             }
