@@ -377,8 +377,8 @@ def run_ours(args):
         layer_ms = {k: float(v) for k, v in zip(names, lt[:7])}
         if table:
             # conv1+conv2 are table reads, not tensor work: the dominant kernel is the conv3 implicit GEMM
-            k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm_kernel<256,relu> (conv3 implicit GEMM, split M tiles)"
-            traffic = ncu_traffic("oz_gemm_kernel<256, 0>", "r1_ncu_t2_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
+            k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm2_kernel (conv3 implicit GEMM, SM pair, split M tiles)"
+            traffic = ncu_traffic("oz_gemm2_kernel", "r1_ncu_final_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
             tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8 - FLOP_CONV2_PER_BOARD_8
             if args.conv3 == "wino":
                 # F(2,3) along y: 4 GEMMs with K = 3C instead of one with 9C -> 2/3 of the direct form's MACs are EXECUTED
@@ -388,12 +388,16 @@ def run_ours(args):
                 tensor_flop_per_eval -= FLOP_CONV3_PER_BOARD_8 // 3
         else:
             k_ms, k_flop, k_name = float(lt[1]), FLOP_CONV2_PER_BOARD_8, "oz_gemm2_kernel (conv2 implicit GEMM, SM pair)"
-            traffic = ncu_traffic("oz_gemm_kernel<256, 0>")
+            traffic = ncu_traffic("oz_gemm2_kernel")
             tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8
         achieved = k_flop * cs * avg_leaves / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         out["roofline"] = {"bound": "tensor", "kernel": k_name,
                            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                            "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": traffic,
+                           "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+                           "note": "peak = cuBLAS bf16 measured back to back for 4 s (power-limited clock); frac > 1 means this "
+                                   "kernel, timed inside a step that also holds lower-power kernels, runs at a higher clock "
+                                   "than cuBLAS sustains - both sit at the 1 kW cap",
                            "avg_boards_per_launch": avg_leaves, "avg_launch_ms": k_ms,
                            "layer_ms": layer_ms, "forwards_timed": int(lt[7]),
                            "tensor_flop_per_eval": tensor_flop_per_eval * cs,

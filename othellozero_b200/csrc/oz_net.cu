@@ -1396,9 +1396,10 @@ static int setup_layer(OzNet* net, OzLayer& Lr, bf16* weights, const float* bias
     rc = make_map_A(&Lr.mapA2, in, cin, iw, ih, bmax, ow, p.split ? oh / 2 : oh, p.split ? 1 : nb);
     if (rc) return rc;
     static const bool allow_2sm = !(getenv("OZ_NET_NO_2SM") && getenv("OZ_NET_NO_2SM")[0] == '1');
-    // measured (B200, 4096 boards): the SM-pair kernel wins on conv2 (0.938 vs 0.955 ms), ties on conv4/fc1/fc2 and loses
-    // on the split-tile conv3 (0.620 vs 0.596 ms) - the step is power-capped, not L2- or SMEM-bound
-    Lr.use_2sm = allow_2sm && epi == EPI_RELU_BF16 && block_n == 256 && !p.split;
+    // measured (B200, 4096 boards, division-free producers): the SM-pair kernel wins everywhere it applies - conv3 (split
+    // tiles) 0.471 vs 0.518 ms, conv4 0.212 vs 0.231, fc1 0.062 vs 0.067: at the power cap the halved B-operand traffic
+    // is clock headroom.  (With the old producer loop, which was the supply limit, the two kernels tied.)
+    Lr.use_2sm = allow_2sm && epi == EPI_RELU_BF16 && block_n == 256;
     if (Lr.use_2sm) {
         rc = make_map_B(&Lr.mapB2, weights, ntaps * ntaps * cin, nout_pad, 128);
         if (rc) return rc;
