@@ -155,6 +155,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// bf16x2 pack with the ReLU fused into the conversion (F2FP.RELU): low half = relu(lo), high half = relu(hi).
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 // Programmatic dependent launch: let the next layer's CTAs start their prologue as ours retire, and make our own
 // first read of the previous layer's output wait for that layer to have completed.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -348,7 +354,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const bool ok = (r < p.rows_valid) && (grow < (long long)L * p.rows_per_board);
             const uint32_t t_row = tmem_base + (uint32_t)(acc * BLOCK_N) + ((uint32_t)(ew * 32) << 16);
             if constexpr (EPI == EPI_RELU_BF16 || EPI == EPI_LINEAR_BF16) {
-                constexpr float LO = (EPI == EPI_RELU_BF16) ? 0.0f : -3.0e38f;
                 bf16* orow = p.out + grow * p.ldc + (long long)n_idx * BLOCK_N;
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -359,14 +364,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         uint32_t packed[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], LO);
-                            float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], LO);
-                            if constexpr (EPI == EPI_LINEAR_BF16) {
-                                packed[j] = pack_pair_fused(a, b);
-                            } else {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                                packed[j] = *reinterpret_cast<uint32_t*>(&h);
-                            }
+                            const float2 bj = *reinterpret_cast<const float2*>(bias + c * 32 + 2 * j);
+                            const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bj);
+                            if constexpr (EPI == EPI_LINEAR_BF16) packed[j] = pack_pair_fused(y.x, y.y);
+                            else packed[j] = pack_relu_bf16x2(y.x, y.y);  // add.f32x2 + one F2FP.RELU per output pair
                         }
                         uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
@@ -623,10 +624,9 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     uint32_t packed[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        float a = fmaxf(__uint_as_float(v[2 * j]) + bias[c * 32 + 2 * j], 0.0f);
-                        float b = fmaxf(__uint_as_float(v[2 * j + 1]) + bias[c * 32 + 2 * j + 1], 0.0f);
-                        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-                        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+                        const float2 bj = *reinterpret_cast<const float2*>(bias + c * 32 + 2 * j);
+                        const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bj);
+                        packed[j] = pack_relu_bf16x2(y.x, y.y);
                     }
                     uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
 #pragma unroll
