@@ -122,17 +122,32 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]; bf16 x bf16 -> fp32, both operands K-major.
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Lean issue path: the MMA warp walks its loop converged and one ELECTED lane issues, which lets the compiler keep the
+// descriptors, TMEM and barrier addresses in uniform registers (with `if (lane == 0)` it re-broadcasts every operand
+// through an ELECT/R2UR loop, ~13 instructions per MMA: enough to pace an N=128 instruction at twice its pipe time).
+// Descriptors are (low word, shared high word): only the start-address field in the low word changes between stages and
+// k steps.
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (SBO), Blackwell descriptor
+// version bit; D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32.
+constexpr uint32_t SW128_DESC_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO, version, SWIZZLE_128B
+__device__ __forceinline__ uint32_t sw128_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -166,16 +181,6 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// Shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
-    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
-    d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
-    return d;
-}
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -269,7 +274,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
+        {  // ===== TMA producer: converged warp, one elected lane issues (operands stay in uniform registers) =====
             pdl_wait();  // the activations we are about to read are the previous kernel's output
             // This one thread feeds the whole pipeline, so its per-stage instruction count is the supply rate: no integer
             // division in the k loop (taps and chunks are nested counters) and everything tile-invariant hoisted.  The
@@ -297,11 +302,14 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
                             const uint32_t fb = full_bar(stage);
                             mbar_wait(empty_bar(stage), phase ^ 1u);
-                            mbar_expect_tx(fb, tx_bytes);
-                            const uint32_t dstA = sA + stage * A_STAGE_BYTES;
-                            tma_load_4d(dstA + offA, &mapA, fb, c0, kx, ky, bA);
-                            if (p.split) tma_load_4d(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
-                            tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            if (elect_one()) {
+                                mbar_expect_tx(fb, tx_bytes);
+                                const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                                tma_load_4d(dstA + offA, &mapA, fb, c0, kx, ky, bA);
+                                if (p.split) tma_load_4d(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
+                                tma_load_2d(sB + stage * B_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            }
+                            __syncwarp();
                             kcol += BLOCK_K;
                             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                         }
@@ -311,8 +319,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer (single thread) =====
+        {  // ===== MMA issuer: the warp walks the loop converged, one elected lane issues (see elect_one) =====
             constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+            const uint32_t a_lo0 = sw128_desc_lo(sA), b_lo0 = sw128_desc_lo(sB);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -322,17 +331,19 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
                     tc_fence_after();
-                    const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
-                    const uint64_t bdesc = make_sw128_desc(sB + stage * B_STAGE_BYTES);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (B_STAGE_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        // advance the start address by k*32 bytes inside the 128-byte swizzle row
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)  // +2 = 32 bytes = 16 bf16 inside the 128-byte swizzle row
+                            umma_bf16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -461,12 +472,14 @@ __device__ __forceinline__ void tmem_relinquish_2sm() {
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_2sm_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(SW128_DESC_HI) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -534,7 +547,7 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier) =====
+        {  // ===== TMA producer (both CTAs; transaction bytes land on the LEADER's full barrier); elected lane issues =====
             pdl_wait();
             // division-free k loop, tile-invariant work hoisted: see the producer of oz_gemm_kernel
             int stage = 0; uint32_t phase = 0;
@@ -559,12 +572,15 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int kx = -p.pad; kx < p.ntaps_x - p.pad; ++kx) {
                         for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
-                            const uint32_t fb = fb0 + 8u * (uint32_t)stage;
-                            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
-                            const uint32_t dstA = sA + stage * A_STAGE_BYTES;
-                            tma_load_4d_2sm(dstA + offA, &mapA, fb, c0, kx, ky, bA);
-                            if (p.split) tma_load_4d_2sm(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
-                            tma_load_2d_2sm(sB + stage * B2_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            if (elect_one()) {
+                                const uint32_t fb = fb0 + 8u * (uint32_t)stage;
+                                if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                                const uint32_t dstA = sA + stage * A_STAGE_BYTES;
+                                tma_load_4d_2sm(dstA + offA, &mapA, fb, c0, kx, ky, bA);
+                                if (p.split) tma_load_4d_2sm(dstA + offH, &mapA2, fb, c0, kx, ky + yH, bH);
+                                tma_load_2d_2sm(sB + stage * B2_STAGE_BYTES, &mapB, fb, kcol, n0);
+                            }
+                            __syncwarp();
                             kcol += BLOCK_K;
                             if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                         }
@@ -574,8 +590,9 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {  // ===== MMA issuer: one thread of the leader CTA drives both tensor cores =====
+        if (rank == 0) {  // ===== MMA issuer: one elected lane of the leader CTA's warp drives both tensor cores =====
             constexpr uint32_t idesc = make_idesc(256, BLOCK_N);
+            const uint32_t a_lo0 = sw128_desc_lo(sA), b_lo0 = sw128_desc_lo(sB);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
@@ -585,15 +602,19 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 for (int kb = 0; kb < p.num_kb; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
-                    const uint64_t bdesc = make_sw128_desc(sB + stage * B2_STAGE_BYTES);
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (B2_STAGE_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                        umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit_2sm(empty_bar(stage), 3);  // frees the stage in BOTH CTAs
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_2sm_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+                        umma_commit_2sm(empty_bar(stage), 3);  // frees the stage in BOTH CTAs
+                    }
+                    __syncwarp();
                     if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit_2sm(tfull_bar(acc), 3);  // accumulator complete -> both epilogues
+                if (elect_one()) umma_commit_2sm(tfull_bar(acc), 3);  // accumulator complete -> both epilogues
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -744,7 +765,7 @@ oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__
     pdl_launch_dependents();
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer (both CTAs; bytes land on the leader's full barrier) =====
+        {  // ===== TMA producer (both CTAs; bytes land on the leader's full barrier); elected lane issues =====
             pdl_wait();
             int stage = 0; uint32_t phase = 0;
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
@@ -759,10 +780,13 @@ oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__
                     for (int kx = 0; kx < 3; ++kx) {
                         for (int c0 = 0; c0 < p.chunks_per_tap * BLOCK_K; c0 += BLOCK_K) {
                             mbar_wait(empty_bar(stage), phase ^ 1u);
-                            const uint32_t fb = fb0 + 8u * (uint32_t)stage;
-                            if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
-                            tma_load_4d_2sm(sA + stage * A_STAGE_BYTES, &mapV, fb, c0, kx, 0, brow);
-                            tma_load_2d_2sm(sB + stage * WB_STAGE_BYTES, &mapU, fb, kcol, urow);
+                            if (elect_one()) {
+                                const uint32_t fb = fb0 + 8u * (uint32_t)stage;
+                                if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+                                tma_load_4d_2sm(sA + stage * A_STAGE_BYTES, &mapV, fb, c0, kx, 0, brow);
+                                tma_load_2d_2sm(sB + stage * WB_STAGE_BYTES, &mapU, fb, kcol, urow);
+                            }
+                            __syncwarp();
                             kcol += BLOCK_K;
                             if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
                         }
@@ -772,8 +796,12 @@ oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader CTA) =====
+        if (rank == 0) {  // ===== MMA issuer (leader CTA) =====
+            // The whole warp walks the loop (so the compiler keeps descriptors and barrier addresses in uniform registers)
+            // and lane 0 issues: an N=128 instruction occupies the tensor pipe for only ~64 clk, so the issue path has to
+            // stay well under that per MMA.
             constexpr uint32_t idesc = make_idesc(256, WINO_N);
+            const uint32_t a_lo0 = sw128_desc_lo(sA), b_lo0 = sw128_desc_lo(sB);
             int stage = 0; uint32_t phase = 0;
             uint32_t tile_phase = 0;
             for (int pt = cluster_id; pt < num_pair_tiles; pt += num_clusters) {
@@ -784,16 +812,20 @@ oz_wino_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__
                     for (int kb = 0; kb < p.num_kb_eta; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
-                        const uint64_t adesc = make_sw128_desc(sA + stage * A_STAGE_BYTES);
-                        const uint64_t bdesc = make_sw128_desc(sB + stage * WB_STAGE_BYTES);
+                        const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+                        const uint32_t b_lo = b_lo0 + (uint32_t)stage * (WB_STAGE_BYTES >> 4);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                            umma_bf16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                        umma_commit_2sm(empty_bar(stage), 3);
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                umma_bf16_2sm_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, idesc, (kb | k) ? 1u : 0u);
+                            umma_commit_2sm(empty_bar(stage), 3);
+                        }
+                        __syncwarp();
                         if (++stage == WSTAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
-                umma_commit_2sm(tfull_bar, 3);  // all four accumulators complete -> both epilogues
+                if (elect_one()) umma_commit_2sm(tfull_bar, 3);  // all four accumulators complete -> both epilogues
+                __syncwarp();
                 tile_phase ^= 1u;
             }
         }
