@@ -1022,39 +1022,50 @@ __global__ void permute_conv2_weights_kernel(const bf16* __restrict__ w /*[co][t
 // accumulation.  Measured alternatives (B200, 4096 boards, C=512): half-row warp items at 62 registers / 32 warps per SM
 // are SLOWER (0.28 vs 0.19 ms: the per-item address arithmetic doubles); masking the odd element instead of the fused
 // pair encoding costs 20 % more instructions for the same time (the kernel is latency-, not issue-bound at 62 % issue).
-template <int NJ>
-__device__ __forceinline__ void t2_square(const uint4* __restrict__ tab, const int* s_pat, int np2, int y, int x, int cpr,
+// EXACT: C == 256 * NJ, i.e. every lane owns NJ full chunks: the chunk guard (a predicated load plus two register-zeroing
+// instructions per load) disappears and the row stride is a compile-time constant.  s_pat holds 9 * pattern (the row
+// index of tap 0).
+// acc + (low 16 bits of w read as bf16), in fp32 (sm_100 mixed-precision add: one FHADD.BF16, no unpacking)
+__device__ __forceinline__ float add_f32_bf16lo(float acc, uint32_t w) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\t}" : "+f"(acc) : "r"(w));
+    return acc;
+}
+template <int NJ, bool EXACT>
+__device__ __forceinline__ void t2_square(const uint4* __restrict__ tab, const int* s_pat, int np2, int y, int x, int cpr_rt,
                                           int lane, const float2 (&bs)[NJ][4], uint4 (&res)[NJ]) {
+    const int cpr = EXACT ? 32 * NJ : cpr_rt;
     uint4 v[9][NJ];
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-        const int pat = s_pat[(y + t / 3) * np2 + (x + t % 3)];  // padded coordinates of (y+ky-1, x+kx-1)
-        const uint4* row = tab + ((size_t)pat * 9 + t) * cpr;
+        const int row9 = s_pat[(y + t / 3) * np2 + (x + t % 3)];  // padded coordinates of (y+ky-1, x+kx-1)
+        const uint4* row = tab + (size_t)(unsigned)((row9 + t) * cpr);
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int ch = lane + 32 * j;
-            v[t][j] = ch < cpr ? __ldg(row + ch) : make_uint4(0, 0, 0, 0);
+            v[t][j] = (EXACT || ch < cpr) ? __ldg(row + ch) : make_uint4(0, 0, 0, 0);
         }
     }
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-        float2 acc[4];
+        // 6 instructions per 16-byte chunk: the even (low-half) elements are added with the mixed-precision
+        // add.f32.bf16 (FHADD.BF16 reads the register half directly - no shift), the odd ones two words at a time with
+        // add.f32x2 on the words themselves (see pack_pair_fused).  Same roundings as shift + fp32 add.
+        float ev[4];
+        float2 od[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = bs[j][i];
+        for (int i = 0; i < 4; ++i) ev[i] = bs[j][i].x;
+        od[0] = make_float2(bs[j][0].y, bs[j][1].y);
+        od[1] = make_float2(bs[j][2].y, bs[j][3].y);
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
             const uint32_t w4[4] = {v[t][j].x, v[t][j].y, v[t][j].z, v[t][j].w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)  // (even, odd) = (low half << 16, the word itself: see pack_pair_fused)
-                acc[i] = __fadd2_rn(acc[i], make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i])));
+            for (int i = 0; i < 4; ++i) ev[i] = add_f32_bf16lo(ev[i], w4[i]);
+            od[0] = __fadd2_rn(od[0], make_float2(__uint_as_float(w4[0]), __uint_as_float(w4[1])));
+            od[1] = __fadd2_rn(od[1], make_float2(__uint_as_float(w4[2]), __uint_as_float(w4[3])));
         }
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[i].x, 0.f), fmaxf(acc[i].y, 0.f));
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        res[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        res[j] = make_uint4(pack_relu_bf16x2(ev[0], od[0].x), pack_relu_bf16x2(ev[1], od[0].y),
+                            pack_relu_bf16x2(ev[2], od[1].x), pack_relu_bf16x2(ev[3], od[1].y));
     }
 }
 
@@ -1078,7 +1089,7 @@ __device__ __forceinline__ uint4 bf8_sub(const uint4& a, const uint4& b) {
 //               top to bottom, keeps the previous two (bf16-rounded) squares in registers and stores the input transform
 //               V [4][Bmax][T][n][C]:  V0 = d0-d2, V1 = d1+d2, V2 = d2-d1 when row 2ty+2 arrives, V3 = d1-d3 at row 2ty+3
 //               (bf16 subtraction of bf16 values: one rounding of the exact difference).
-template <int NJ, bool WINO>  // 16-byte chunks per lane: C = 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
+template <int NJ, bool WINO, bool EXACT>  // 16-byte chunks per lane: C <= 256 * NJ (C = 128: NJ = 1, upper half-warp idle)
 __global__ void __launch_bounds__(256, 2)
 conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ opp, const int* __restrict__ count,
                           int max_count, int n, int C, const bf16* __restrict__ table2, const float* __restrict__ bias,
@@ -1089,14 +1100,14 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
     if (L > max_count) L = max_count;
     const int nsq = n * n, np2 = n + 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cpr = C >> 3;  // 16-byte chunks per row
+    const int cpr = EXACT ? 32 * NJ : (C >> 3);  // 16-byte chunks per row
     float2 bs[NJ][4];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int ch = lane + 32 * j;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            bs[j][i] = ch < cpr ? make_float2(bias[ch * 8 + 2 * i], bias[ch * 8 + 2 * i + 1]) : make_float2(0.f, 0.f);
+            bs[j][i] = (EXACT || ch < cpr) ? make_float2(bias[ch * 8 + 2 * i], bias[ch * 8 + 2 * i + 1]) : make_float2(0.f, 0.f);
     }
     const uint4* tab = reinterpret_cast<const uint4*>(table2);
     for (int b = blockIdx.x; b < L; b += gridDim.x) {
@@ -1104,7 +1115,7 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
         if (threadIdx.x < np2 * np2) {
             const int py = threadIdx.x / np2, px = threadIdx.x - py * np2;
             const int y = py - 1, x = px - 1;
-            int pat = N_PATTERNS;
+            int pat = N_PATTERNS;  // stored as 9 * pattern = row index of tap 0 in table2
             if (y >= 0 && y < n && x >= 0 && x < n) {
                 pat = 0;
                 int mul = 1;
@@ -1120,19 +1131,19 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
                     mul *= 3;
                 }
             }
-            s_pat[threadIdx.x] = pat;
+            s_pat[threadIdx.x] = pat * 9;
         }
         __syncthreads();
         if constexpr (!WINO) {
             for (int pos = warp; pos < nsq; pos += 8) {
                 const int y = pos / n, x = pos - y * n;
                 uint4 res[NJ];
-                t2_square<NJ>(tab, s_pat, np2, y, x, cpr, lane, bs, res);
+                t2_square<NJ, EXACT>(tab, s_pat, np2, y, x, cpr, lane, bs, res);
                 uint4* orow = reinterpret_cast<uint4*>(out + ((size_t)b * nsq + pos) * C);
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     const int ch = lane + 32 * j;
-                    if (ch < cpr) orow[ch] = res[j];
+                    if (EXACT || ch < cpr) orow[ch] = res[j];
                 }
             }
         } else {
@@ -1144,7 +1155,7 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
 #pragma unroll 1
                 for (int y = 0; y < n; ++y) {
                     uint4 cur[NJ];
-                    t2_square<NJ>(tab, s_pat, np2, y, x, cpr, lane, bs, cur);
+                    t2_square<NJ, EXACT>(tab, s_pat, np2, y, x, cpr, lane, bs, cur);
                     if (y >= 2) {
                         if (!(y & 1)) {
                             const int ty = (y - 2) >> 1;
@@ -1152,7 +1163,7 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
 #pragma unroll
                             for (int j = 0; j < NJ; ++j) {
                                 const int ch = lane + 32 * j;
-                                if (ch < cpr) {
+                                if (EXACT || ch < cpr) {
                                     v0[ch] = bf8_sub(p2[j], cur[j]);
                                     v0[eta_stride + ch] = bf8_add(p1[j], cur[j]);
                                     v0[2 * eta_stride + ch] = bf8_sub(cur[j], p1[j]);
@@ -1164,7 +1175,7 @@ conv2_table_gather_kernel(const u64* __restrict__ own, const u64* __restrict__ o
 #pragma unroll
                             for (int j = 0; j < NJ; ++j) {
                                 const int ch = lane + 32 * j;
-                                if (ch < cpr) v3[ch] = bf8_sub(p2[j], cur[j]);
+                                if (EXACT || ch < cpr) v3[ch] = bf8_sub(p2[j], cur[j]);
                             }
                         }
                     }
@@ -1643,13 +1654,10 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         int blocks = max_count < net->sm_count * 2 ? max_count : net->sm_count * 2;  // 2 resident CTAs/SM, grid-stride
         const bf16* t2 = net->table2; const float* b2 = net->bias[0];
         unsigned long long* ts = trace_slot(net, "gather");
-#define OZ_T2(NJ)                                                                                                      \
-    if (net->conv3_wino)                                                                                               \
-        conv2_table_gather_kernel<NJ, true><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, \
-                                                                    b2, net->v3, net->Bmax, ts);                      \
-    else                                                                                                               \
-        conv2_table_gather_kernel<NJ, false><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, \
-                                                                     b2, net->act2, net->Bmax, ts)
+#define OZ_T2K(NJ, W, X, OUT) conv2_table_gather_kernel<NJ, W, X><<<blocks, 256, 0, st>>>(own_dev, opp_dev, count_dev, max_count, n, C, t2, b2, OUT, net->Bmax, ts)
+#define OZ_T2(NJ)                                                                  \
+    if (net->conv3_wino) { if (C == 256 * NJ) OZ_T2K(NJ, true, true, net->v3); else OZ_T2K(NJ, true, false, net->v3); } \
+    else { if (C == 256 * NJ) OZ_T2K(NJ, false, true, net->act2); else OZ_T2K(NJ, false, false, net->act2); }
         switch (C / 256) {
             case 0: case 1: OZ_T2(1); break;
             case 2: OZ_T2(2); break;
@@ -1657,6 +1665,7 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
             default: OZ_T2(4); break;
         }
 #undef OZ_T2
+#undef OZ_T2K
         OZ_CUDA(cudaGetLastError());
         e->launches++;
         if (tm) cudaEventRecord(ev[2], st);
