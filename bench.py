@@ -409,9 +409,9 @@ def run_ours(args):
                 "bound": "hbm", "kernel": "conv2_table_gather_kernel (conv1+conv2 as 484 table-row reads per board)",
                 "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
                 "avg_launch_ms": float(lt[1]),
-                "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_t2_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
+                "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_final_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
                 "note": "frac > 1 means the rows are served by L2/L1, not HBM (ncu: DRAM reads ~4 % of the algorithmic bytes); "
-                        "the kernel is latency-bound at ~62 % issue"}
+                        "the kernel is latency-bound at ~44 % issue"}
     else:
         out["roofline"] = {"bound": "hbm", "kernel": "tree_step_kernel", "achieved": sims_per_s / world * 1000 / 1e9,
                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sims_per_s / world * 1000 / 1e9 / peaks["hbm_gbs"],
