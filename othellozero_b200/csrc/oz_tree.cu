@@ -346,6 +346,8 @@ __device__ __forceinline__ void warp_argmax(double& u, int& j) {
 // latency-bound kernel; capped at 64 registers (~0.4 KB of spills per thread, L1-resident) all games are resident at once:
 // rules+tree workload 2.20e8 -> 2.49e8 sims/s, tree share of the self-play step 0.038 -> 0.030 ms (ncu: 1867 warp
 // instructions per simulation, issue 39 %, stalls dominated by instruction fetch and fixed-latency waits, not DRAM).
+// Turning the big helpers (play_move, table_find, expand_and_backup, backup_path) into real calls shrinks the kernel from
+// ~10 K to 6.8 K SASS instructions but is slower (2.30e8): pointer arguments force positions and paths into local memory.
 __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzTreeParams P) {
     __shared__ double s_a[TREE_WARPS][64];
     const int lane = threadIdx.x & 31;
