@@ -236,10 +236,14 @@ def run_ours(args):
         torch.cuda.synchronize()
         eng.load_weights_from_tensor(wt, C)
         eng.set_timing(True)
-    first_id = rank * G
-    sb, sw, sp = synthetic_starts(E, G, args.seed, first_id, local)
-    ids = np.arange(first_id, first_id + G, dtype=np.uint64)
-    eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
+    # The timed region always finds G games in flight: with the default K/W every game is still in its opening, and for a
+    # long run (K + W beyond ~40 moves, where episodes start to end) the device-side queue refills the slots, so `value`
+    # degrades into the steady-state mix of game phases instead of into idle slots.
+    total = G * (1 + (args.steps + args.warmup) // 40)
+    first_id = rank * total
+    sb, sw, sp = synthetic_starts(E, total, args.seed, first_id, local)
+    ids = np.arange(first_id, first_id + total, dtype=np.uint64)
+    eng.selfplay_begin(total, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
 
     stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{local}")
     tree_only = mode == E.PRIOR_HASH
@@ -247,7 +251,7 @@ def run_ours(args):
 
     def tree_batch():
         # hash priors: a whole game runs inside ONE tree kernel launch, so a step is one complete batch of games
-        eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
+        eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb[:G], sw[:G], sp[:G], ids[:G])
         eng.selfplay_run(-1)
         return eng.counters()
 
@@ -358,7 +362,7 @@ def run_ours(args):
                    "step": (f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
                             if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 432 / 1e9),
-                   "starts": "initial position + (game_id % 8) random plies", "parallelism": f"games sharded x{world}"},
+                   "starts": "initial position + (game_id % 8) random plies", "games_queued_per_gpu": int(total), "parallelism": f"games sharded x{world}"},
         "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
         "net_evals_per_s": tot_nodes / (ms / 1e3), "evals_per_sim": tot_nodes / max(1.0, tot_sims),
         "eval_cache": {"log2_entries": args.eval_cache_log2, "hits": int(tot_hits), "same_step_shares": int(tot_alias),
