@@ -100,7 +100,7 @@ int oz_rules_score_dev(const uint64_t* black, const uint64_t* white, int32_t* bl
 
 /* ---- perft / random playouts: RandomOthelloAgent loop, agents.py:20-24,71-84 ------------- */
 /* Game g (global id first_game_id+g) starts at initial_board(board_size) and plays
- * legal[mulhi32(sm64(sm64(seed ^ id) + p) >> 32, popcount(legal))] at move index p (ascending bit order ==
+ * legal[mulhi32(sm64(sm64(sm64(seed) + id) + p) >> 32, popcount(legal))] at move index p (ascending bit order ==
  * row-major), with auto-pass/terminal as OthelloGame.play, for at most max_moves moves (<0: to the end).
  * info[g] = plies | player<<8 | finished<<9 | passes<<16.  moves (optional) = [n_games][64] squares, 0xFF padded. */
 int oz_perft_playouts_host(int32_t device, int32_t board_size, uint64_t seed, uint64_t first_game_id,
@@ -146,9 +146,16 @@ int oz_search_get_status(oz_engine* e, int32_t* status);
 int oz_engine_counters(oz_engine* e, uint64_t* out8);
 
 /* ---- self-play: training.execute_episode (training.py:26-72) ------------------------------ */
-/* Starts n_games episodes (start positions as oz_search_reset).  temperature > 0: the greedy action is the
- * first arg-max of the visit counts (training.py:48-53); with probability 1-e_greedy a uniformly random legal
- * action from the engine RNG is played instead (training.py:55-56; CPython's RNG stream is not reproduced).
+/* Starts n_games episodes (start positions as oz_search_reset; a start whose side to move has no legal move is
+ * rejected with OZ_ERR_INVALID).  temperature > 0: the greedy action is the first arg-max of the visit counts
+ * (training.py:48-53).  temperature == 0 (the reference's setting from iteration `temperature_threshold` on,
+ * main.py:73-76): the policy is one-hot on random.choice over the arg-max set (othelo_mcts.py:54-62) - a unique maximum
+ * needs no draw, ties are drawn from the engine RNG.  With probability 1-e_greedy a uniformly random legal action is
+ * played instead (training.py:55-56).  CPython's RNG stream is not reproduced; the engine's counter RNG is:
+ *   base = sm64(sm64(seed ^ 0x5EEDC01D) + game_id); draw(p, w) = sm64(base + 4p + w) at move index p;
+ *   tie-break tied[mulhi32(draw(p,2) >> 32, len(tied))] (row-major), coin (draw(p,0) >> 11) * 2^-53 <= e_greedy,
+ *   random action legal[mulhi32(draw(p,1) >> 32, len(legal))].
+ * tests/golden/episodes_rng.json holds the reference's own execute_episode run with these draws injected.
  * max_moves < 0: play to the end.
  * n_games may exceed max_games (a game QUEUE): the first max_games episodes start at once and a slot whose episode ends
  * takes the next queued game (fresh tree, its own RNG stream keyed by its game id, default id = game index), so the leaf
@@ -163,7 +170,9 @@ int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* black, cons
 int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active);
 /* Per-move records of EVERY game of the job (queued ones included, indexed by game), HOST buffers sized [n_games][64]
  * (rec_visits [n_games][64][64], may be NULL unless log_visits): position before the move as black/white bitboards, action square bit, mover; n_moves,
- * winner (0 BLACK / 1 WHITE, draw -> BLACK, Othello/__init__.py:254-256; -1 unfinished) per game. */
+ * winner (0 BLACK / 1 WHITE, draw -> BLACK, Othello/__init__.py:254-256; -1 unfinished) per game.
+ * Entry n_moves[g] (< 64) of rec_black/rec_white[g] holds the position the episode ended in (the board every example
+ * of the reference aliases, training.py:63). */
 int oz_selfplay_get_records(oz_engine* e, uint64_t* rec_black, uint64_t* rec_white, uint8_t* rec_action,
                             uint8_t* rec_player, int32_t* n_moves, int32_t* winner, int32_t* rec_visits);
 /* Current positions of the min(n_games, max_games) slots (HOST buffers; any may be NULL). */

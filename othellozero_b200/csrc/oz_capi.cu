@@ -47,6 +47,18 @@ __global__ void scatter_priors_kernel(float* __restrict__ dst, const float* __re
     dst[(size_t)l * 64 + f] = src[i];
 }
 
+// Start positions of a self-play job: *bad = lowest index of a position that cannot be played.
+__global__ void validate_starts_kernel(int n_games, const u64* __restrict__ black, const u64* __restrict__ white,
+                                       const int* __restrict__ player, u64 full, int* bad) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_games) return;
+    const u64 b = black[g], w = white[g];
+    const int pl = player ? player[g] : 0;
+    const bool ok = !(b & w) && !((b | w) & ~full) && (pl == 0 || pl == 1) &&
+                    ozbb::legal_moves(pl ? w : b, pl ? b : w, full) != 0ull;
+    if (!ok) atomicMin(bad, g);
+}
+
 // ---- engine -----------------------------------------------------------------------------------------
 extern "C" int oz_engine_create(const oz_engine_config* cfg, oz_engine** out) {
     OZ_REQUIRE(cfg && out, "null argument");
@@ -313,7 +325,7 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
                                  double e_greedy, int32_t max_moves) {
     OZ_REQUIRE(e, "null engine");
     OZ_REQUIRE(num_sims >= 2, "num_sims must be >= 2 (with 1 the reference's policy is all-zero, training.py:48-53)");
-    OZ_REQUIRE(temperature > 0.0, "device self-play needs temperature > 0 (T=0 draws random.choice, othelo_mcts.py:54-62)");
+    OZ_REQUIRE(temperature >= 0.0, "temperature must be >= 0 (got %g)", temperature);
     OZ_REQUIRE(e_greedy >= 0.0 && e_greedy <= 1.0, "e_greedy must be in [0,1]");
     if (e->cfg.prior_mode == OZ_PRIOR_HOST) { oz_set_error("self-play needs OZ_PRIOR_HASH or OZ_PRIOR_NET"); return OZ_ERR_STATE; }
     OZ_REQUIRE(n_games >= 1, "n_games must be >= 1 (got %d)", n_games);
@@ -325,14 +337,17 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
     rc = oz_tree_reset(e, slots, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
     if (rc) return rc;
     OzTreeParams& P = e->tp;
-    if (e->q_buf) { OZ_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(e->q_buf); e->q_buf = nullptr; }
+    e->search_started = false;
     P.q_black = P.q_white = nullptr; P.q_player = nullptr; P.q_ids = nullptr;
-    if (n_games > slots && (black || player || game_ids)) {
+    if (black || player || game_ids) {  // staged for the whole job: validated below, and the queue reads them
         const size_t g8 = ((size_t)n_games * 8 + 255) & ~(size_t)255, g4 = ((size_t)n_games * 4 + 255) & ~(size_t)255;
-        unsigned char* q = nullptr;
-        cudaError_t qerr = cudaMalloc((void**)&q, 3 * g8 + g4);
-        if (qerr != cudaSuccess) { oz_set_error("cudaMalloc for %d queued games failed: %s", n_games, cudaGetErrorString(qerr)); return OZ_ERR_NOMEM; }
-        e->q_buf = q;
+        if (3 * g8 + g4 > e->q_bytes) {  // grow-only staging buffer
+            if (e->q_buf) { OZ_CUDA(cudaStreamSynchronize(e->stream)); cudaFree(e->q_buf); e->q_buf = nullptr; e->q_bytes = 0; }
+            cudaError_t qerr = cudaMalloc(&e->q_buf, 3 * g8 + g4);
+            if (qerr != cudaSuccess) { oz_set_error("cudaMalloc for %d queued games failed: %s", n_games, cudaGetErrorString(qerr)); return OZ_ERR_NOMEM; }
+            e->q_bytes = 3 * g8 + g4;
+        }
+        unsigned char* q = (unsigned char*)e->q_buf;
         if (black) {
             OZ_CUDA(cudaMemcpyAsync(q, black, (size_t)n_games * 8, cudaMemcpyHostToDevice, e->stream));
             OZ_CUDA(cudaMemcpyAsync(q + g8, white, (size_t)n_games * 8, cudaMemcpyHostToDevice, e->stream));
@@ -347,12 +362,28 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
             P.q_player = (const int*)(q + 3 * g8);
         }
     }
+    if (black) {
+        // a start whose side to move has no legal move would never reach a move transition (MCTS.simulate of a root
+        // without actions): refuse the job instead of silently dropping the game
+        int* bad = e->tp.leaf_count + 3;
+        e->h_pinned[6] = 0x7fffffff;
+        OZ_CUDA(cudaMemcpyAsync(bad, &e->h_pinned[6], sizeof(int), cudaMemcpyHostToDevice, e->stream));
+        validate_starts_kernel<<<(n_games + 255) / 256, 256, 0, e->stream>>>(n_games, P.q_black, P.q_white, P.q_player, P.full, bad);
+        OZ_CUDA(cudaGetLastError());
+        e->launches++;
+        OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[6], bad, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+        OZ_CUDA(cudaStreamSynchronize(e->stream));
+        OZ_REQUIRE(e->h_pinned[6] == 0x7fffffff,
+                   "start position %d is not playable (overlapping / off-board discs, or the side to move has no legal move)",
+                   e->h_pinned[6]);
+    }
     P.total_games = n_games;
     e->rec_games = n_games;
     P.selfplay = 1;
     P.num_sims = num_sims;
     P.max_moves = max_moves;
     P.e_greedy = e_greedy;
+    P.temperature = temperature;
     e->h_pinned[1] = slots;
     e->h_pinned[5] = slots;  // next queued game
     OZ_CUDA(cudaMemcpyAsync(P.n_active, &e->h_pinned[1], sizeof(int), cudaMemcpyHostToDevice, e->stream));

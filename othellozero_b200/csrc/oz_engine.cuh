@@ -81,7 +81,7 @@ struct OzTreeParams {
     u64* cache_tags; u64* cache_keys; int* cache_leaf; float* cache_pi; float* cache_v; int* leaf_cache_idx;
     int cache_log2_buckets;
     // self-play
-    int num_sims; int max_moves; double e_greedy; u64 seed;
+    int num_sims; int max_moves; double e_greedy; double temperature; u64 seed;
     u64* rec_black; u64* rec_white; unsigned char* rec_action; unsigned char* rec_player; int* rec_visits;
     int* rec_nmoves;  // [record capacity] plies played so far, by game index
     // game queue: a slot whose episode ends starts game *next_game (while < total_games) - self-play keeps the leaf batch
@@ -112,7 +112,8 @@ struct oz_engine {
     int rec_games = 0;         // games whose records the last oz_selfplay_begin covers (>= n_games slots with a queue)
     size_t rec_capacity = 0;   // games the record buffers hold (grown on demand, see oz_tree_reserve_records)
     void* rec_buf = nullptr;   // one allocation behind tp.rec_* / tp.winner / tp.rec_nmoves
-    void* q_buf = nullptr;     // queued start positions of the current self-play job
+    void* q_buf = nullptr;     // queued start positions of the current self-play job (grow-only)
+    size_t q_bytes = 0;
     unsigned char* scratch = nullptr;  // persistent device staging for the host-buffer entry points (no per-call
     size_t scratch_bytes = 0;          // cudaMallocAsync/FreeAsync: measured 2-350 ms per call when the pool is trimmed)
     // device allocations (freed in destroy)

@@ -63,7 +63,7 @@ perft_playout_kernel(int n, u64 full, u64 seed, u64 first_id, long long n_games,
         u64 own, opp;
         initial_position(n, &own, &opp);  // BLACK to move: own = black
         u32 player = 0, plies = 0, passes = 0, finished = 0;
-        u64 base = sm64(seed ^ (first_id + (u64)g));
+        u64 base = stream_key(seed, first_id + (u64)g);
         u64 legal = legal_moves(own, opp, full);
         unsigned char* mv = moves ? moves + g * 64 : nullptr;
         while (legal && (max_moves < 0 || (int)plies < max_moves)) {

@@ -435,10 +435,19 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
                 if (cnt > best) { best = cnt; bj = j; }
             }
             warp_argmax(best, bj);
-            u64 base = sm64(P.seed ^ P.game_id[slot] ^ 0x5EEDC01Dull);
-            double coin = (double)(sm64(base + 2ull * (u64)ply) >> 11) * (1.0 / 9007199254740992.0);
+            const u64 base = episode_key(P.seed, P.game_id[slot]);
             int aj = bj;
-            if (!(coin <= P.e_greedy)) aj = (int)pick_index(sm64(base + 2ull * (u64)ply + 1ull), (u32)k);
+            if (P.temperature == 0.0) {
+                // othelo_mcts.py:54-62: the policy is one-hot on random.choice(arg-max set); a unique maximum needs no
+                // draw, ties are broken by the game's counter RNG over the tied actions in row-major order
+                const unsigned t0 = __ballot_sync(FULLW, lane < k && (double)(Np[lane] & N_MASK) == best);
+                const unsigned t1 = __ballot_sync(FULLW, lane + 32 < k && (double)(Np[lane + 32] & N_MASK) == best);
+                const u64 ties = (u64)t0 | ((u64)t1 << 32);
+                const int nt = popc(ties);
+                if (nt > 1) aj = kth_set_bit(ties, (int)pick_index(episode_draw(base, ply, DRAW_TIE_BREAK), (u32)nt));
+            }
+            const double coin = (double)(episode_draw(base, ply, DRAW_COIN) >> 11) * (1.0 / 9007199254740992.0);
+            if (!(coin <= P.e_greedy)) aj = (int)pick_index(episode_draw(base, ply, DRAW_RANDOM_ACTION), (u32)k);
             int sq = kth_set_bit(legal, aj);
             if (ply < 64) {
                 size_t ri = (size_t)gi * 64 + ply;
@@ -464,7 +473,12 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
             if (lane == 0) P.rec_nmoves[gi] = ply;
             const bool over = (fl & MOVE_FINISHED) != 0;
             if (over || (P.max_moves >= 0 && ply >= P.max_moves)) {
-                if (lane == 0) P.winner[gi] = over ? ((popc(black) >= popc(white)) ? 0 : 1) : -1;
+                if (lane == 0) {
+                    P.winner[gi] = over ? ((popc(black) >= popc(white)) ? 0 : 1) : -1;
+                    if (ply < 64) {  // entry n_moves of a game's record row = the position the episode ended in
+                        P.rec_black[(size_t)gi * 64 + ply] = black; P.rec_white[(size_t)gi * 64 + ply] = white;
+                    }
+                }
                 // the episode is over: take the next queued game into this slot, or retire the slot
                 int ng = P.total_games;
                 if (lane == 0) ng = atomicAdd(P.next_game, 1);

@@ -12,6 +12,7 @@ SURVEY §0.8); with e_greedy < 1 the random moves come from the engine's counter
 from __future__ import annotations
 
 import logging
+import os
 import threading
 import uuid
 
@@ -19,21 +20,17 @@ import numpy as np
 
 from . import engine as _e
 from .mcts import HashPriorNet
-from .net import B200NNet, bits_to_board
+from .net import B200NNet
 
 
 def training_example_symmetries(board, policy):
-    """training.py:13-23 (same order: rotations 1..4, flipped first)."""
-    out = []
-    for rotation in range(1, 5):
-        for flip in (True, False):
-            b = np.rot90(board, k=rotation)
-            p = np.rot90(policy, k=rotation)
-            if flip:
-                b = np.fliplr(b)
-                p = np.fliplr(p)
-            out.append((b, p))
-    return out
+    """The 8 symmetric copies in the order of training.py:13-23: for 1..4 quarter turns, the mirrored copy first."""
+    pairs = []
+    for quarter_turns in (1, 2, 3, 4):
+        rb, rp = np.rot90(board, quarter_turns), np.rot90(policy, quarter_turns)
+        pairs.append((np.fliplr(rb), np.fliplr(rp)))
+        pairs.append((rb, rp))
+    return pairs
 
 
 getSymmetries = training_example_symmetries  # alpha-zero-general name (SURVEY Appendix D)
@@ -79,28 +76,26 @@ class SelfPlay:
 
 
 def records_to_examples(rec: dict, game: int, board_size: int, reference_aliasing: bool = False):
-    """One game's records -> the reference's example list (training.py:58-72)."""
+    """One game's records -> the reference's example list (training.py:58-72): per move the 8 symmetries of
+    (board (N,N,2) bool, one-hot policy (N,N) float64) in the order of training.py:13-23, with z = +1 iff the mover won.
+
+    reference_aliasing=True reproduces the reference's stream byte for byte: its examples hold VIEWS of the live board
+    (training.py:63 appends np.rot90 / np.fliplr views of game.board()), so once the episode is over every example shows
+    the final position.  The final position is entry n_moves of the record row (include/oz_b200.h)."""
     n = board_size
     k = int(rec["n_moves"][game])
     winner = int(rec["winner"][game])
     examples = []
-    final_board = None
-    if reference_aliasing and k:
-        # every example of the reference is a view of the live board, i.e. shows the FINAL position
-        last = k - 1
-        fb = bits_to_board(rec["black"][game][last], rec["white"][game][last], n)
-        from .othello import OthelloGame, OthelloPlayer
-        a = int(rec["action"][game][last])
-        pl = OthelloPlayer.BLACK if int(rec["player"][game][last]) == 0 else OthelloPlayer.WHITE
-        OthelloGame.flip_board_squares(fb, pl, a >> 3, a & 7)
-        final_board = fb
+    if reference_aliasing:
+        final_board = bits_to_boards(rec["black"][game][k:k + 1], rec["white"][game][k:k + 1], n)[0]
+    else:
+        boards = bits_to_boards(rec["black"][game][:k], rec["white"][game][:k], n)
     for p in range(k):
-        board = final_board if reference_aliasing else bits_to_board(rec["black"][game][p], rec["white"][game][p], n)
+        board = final_board if reference_aliasing else boards[p]
         a = int(rec["action"][game][p])
         policy = np.zeros((n, n))
         policy[a >> 3][a & 7] = 1
-        player = int(rec["player"][game][p])
-        z = 1 if winner == player else -1
+        z = 1 if winner == int(rec["player"][game][p]) else -1
         for b, pol in training_example_symmetries(board, policy):
             examples.append((b, pol, z))
     return examples
@@ -147,11 +142,35 @@ def records_to_examples_batch(rec: dict, board_size: int, games=None):
     return out
 
 
+# ---- RNG streams of episodes -------------------------------------------------------------------------------------
+# The reference draws from CPython's process-global, time-seeded RNG, so no two episodes ever share randomness.  Here an
+# episode's stream is keyed by (seed, game id) (include/oz_b200.h): by default the seed is drawn once per process from
+# the OS and game ids come from a process-wide allocator, so consecutive calls, consecutive WorkerManager.run()s and
+# different workers (one per GPU) never replay a stream.  Pass seed= / game_ids= for reproducible runs.
+_PROCESS_SEED = int.from_bytes(os.urandom(8), "little")
+_ids_lock = threading.Lock()
+_next_game_id = 0
+
+
+def allocate_game_ids(n: int) -> np.ndarray:
+    """A block of n game ids never handed out before in this process."""
+    global _next_game_id
+    with _ids_lock:
+        first = _next_game_id
+        _next_game_id += int(n)
+    return np.arange(first, first + int(n), dtype=np.uint64)
+
+
 def execute_episodes(n_episodes, board_size, neural_network, degree_exploration, num_simulations, policy_temperature,
-                     e_greedy, device: int = 0, seed: int = 0, reference_aliasing: bool = False, game_ids=None,
+                     e_greedy, device: int = 0, seed: int | None = None, reference_aliasing: bool = False, game_ids=None,
                      max_concurrent: int = 4096):
     """n_episodes x training.execute_episode as one GPU job; returns a list of example lists.  At most `max_concurrent`
-    episodes are in flight (node pools are per slot); the others are queued on the device and start as slots free up."""
+    episodes are in flight (node pools are per slot); the others are queued on the device and start as slots free up.
+    policy_temperature may be 0 (main.py:73-76 switches to it after `temperature_threshold` iterations)."""
+    if seed is None:
+        seed = _PROCESS_SEED
+    if game_ids is None:
+        game_ids = allocate_game_ids(n_episodes)
     sp = SelfPlay(board_size, neural_network, degree_exploration, max_games=min(n_episodes, max_concurrent),
                   num_simulations=num_simulations, device=device, seed=seed)
     try:
@@ -203,9 +222,11 @@ class Worker:
         return f'{self.__class__.__name__}-{str(uuid.uuid4()).split("-", 1)[0]}'
 
 
-def make_b200_worker(worker_base=Worker, device: int = 0, seed: int = 0):
+def make_b200_worker(worker_base=Worker, device: int = 0, seed: int | None = None):
     """Builds a ``B200Worker`` class deriving from ``worker_base`` — pass the reference's ``workers.Worker`` so that
-    ``WorkerManager.add_worker``'s isinstance check (workers.py:186-190) accepts it."""
+    ``WorkerManager.add_worker``'s isinstance check (workers.py:186-190) accepts it.  seed=None (default): the
+    process-wide OS-drawn seed; game ids always come from the process-wide allocator, so every run() of every worker
+    plays episodes nobody has played before (see allocate_game_ids)."""
 
     class B200Worker(worker_base):
         def __init__(self):

@@ -108,3 +108,20 @@ def test_np_sum_matches_numpy():
             a = rng.random(n) * (rng.random(n) < 0.3)
             side = int(round(n ** 0.5))
             assert oracle.np_sum(a) == float(np.sum(a.reshape(side, side)))
+
+
+def test_rng_episodes_golden(golden_rng_episodes):
+    """The reference's OWN execute_episode (training.py:26-72), run with the engine's counter RNG injected into its three
+    draw sites (tools/gen_golden.py::EngineRng): temperature 0 with random.choice over tied arg-max actions
+    (othelo_mcts.py:54-62), the e-greedy coin and the random legal action (training.py:51-56)."""
+    import prior_fns
+    ties = 0
+    for rec in golden_rng_episodes:
+        predict = None if rec["prior"] == "hash" else prior_fns.sha_prior
+        out = oracle.execute_episode(rec["n"], rec["sims"], c=rec["c"], temperature=rec["T"], e_greedy=rec["e_greedy"],
+                                     predict=predict, seed=rec["seed"], game_id=rec["game_id"])
+        assert out["moves"] == rec["moves"], rec
+        assert [1 if out["winner"] == p else -1 for p in out["players"]] == rec["z"]
+        assert out["net_calls"] == rec["net_calls"]
+        ties += rec["rng_calls"]["ties"]
+    assert ties > 50  # the tie-break draw really decided moves
