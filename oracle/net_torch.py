@@ -6,8 +6,12 @@ same,same,valid,valid; BatchNormalization(axis=channels, eps=1e-3) in inference 
 statistics); Flatten in (h,w,c) order; Dense 1024 / 512 with BN + ReLU (dropout inactive in
 predict, Net/NNet.py:85); heads Dense(N^2, softmax) and Dense(1, tanh).
 
-PARITY UNPINNED: TensorFlow/Keras are not installed, so the reference's own network cannot be run
-to pin this restatement; the 1e-2 check compares the CUDA tower with this file on identical weights.
+PARITY STATUS: TensorFlow/Keras are not installed, so no execution of the reference's own network pins
+this restatement ("parity unpinned" against a Keras run).  What pins it instead: an independent NumPy
+restatement written from the Keras layer definitions (oracle/net_numpy.py) must agree with this file to
+1e-5, and both must reproduce hand-derived known answers for kernel orientation, padding, flatten order,
+Dense layout and the BN epsilon (tests/test_net_oracle_pin_cpu.py, tests/kat_net.py).  The 1e-2 check
+compares the CUDA tower with this file on identical weights.
 The weight blob layout is defined by this file independently of the product (Keras get_weights()
 order) so that a layout mistake on either side shows up as a mismatch.
 """

@@ -1547,11 +1547,16 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
     }
     // stage the blob on the device
     const float* d = blob;
-    float* staged = nullptr;
+    struct Staged {  // freed on every return path (the OZ_CUDA macros return early)
+        float* p = nullptr;
+        cudaStream_t st;
+        ~Staged() { if (p) { cudaStreamSynchronize(st); cudaFree(p); } }
+    } staged;
+    staged.st = st;
     if (!on_device) {
-        OZ_CUDA(cudaMalloc((void**)&staged, (size_t)need * 4));
-        OZ_CUDA(cudaMemcpyAsync(staged, blob, (size_t)need * 4, cudaMemcpyHostToDevice, st));
-        d = staged;
+        OZ_CUDA(cudaMalloc((void**)&staged.p, (size_t)need * 4));
+        OZ_CUDA(cudaMemcpyAsync(staged.p, blob, (size_t)need * 4, cudaMemcpyHostToDevice, st));
+        d = staged.p;
     }
     const float eps = 1e-3f;  // keras BatchNormalization default epsilon
     const float* q = d;
@@ -1622,7 +1627,6 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         e->launches += 2;
     }
     OZ_CUDA(cudaStreamSynchronize(st));
-    if (staged) OZ_CUDA(cudaFree(staged));
     net->loaded = true;
     return OZ_OK;
 }

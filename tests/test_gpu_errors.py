@@ -26,7 +26,11 @@ def test_invalid_arguments_raise_like_the_reference():
     with pytest.raises(AssertionError):
         e.selfplay_begin(2, 1)                    # num_sims = 1: the reference's policy would be all-zero
     with pytest.raises(AssertionError):
-        e.selfplay_begin(2, 10, temperature=0.0)  # T = 0 needs random.choice on the host
+        e.selfplay_begin(2, 10, temperature=-1.0)
+    with pytest.raises(AssertionError):           # a start whose side to move cannot move (here: an empty board)
+        e.selfplay_begin(2, 10, black=[0x0000001008000000, 0], white=[0x0000000810000000, 0], player=[0, 0])
+    with pytest.raises(AssertionError):           # overlapping discs
+        e.selfplay_begin(1, 10, black=[0x0000001818000000], white=[0x0000000810000000], player=[0])
     with pytest.raises(_lib.OzError):
         e.net_forward([1], [2])                   # no network in this engine
     with pytest.raises(AssertionError):

@@ -252,3 +252,51 @@ def test_batched_arena_drivers_and_worker_work_types():
     assert len(ev) == 2 and all(0 <= x <= 5 for x in ev)
     with pytest.raises(TypeError):
         w._run("no such work", 1, (), {})
+
+
+# ---- example stream at the drop-in boundary, against the reference's own stream ----------------------------------------
+def test_execute_episode_stream_equals_reference_digest(golden_examples):
+    """selfplay.execute_episodes (device self-play -> records -> examples) must reproduce training.execute_episode's list
+    byte for byte: the digests were taken from the reference's own output (tools/gen_golden.py examples), with the
+    engine's draws injected for T = 0 / e_greedy < 1."""
+    from example_digest import examples_digest
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.selfplay import execute_episodes
+    done = 0
+    for g in golden_examples:
+        if g["prior"] != "hash":
+            continue  # host-evaluated priors: covered through the oracle in tests/test_examples_reference_cpu.py
+        kw = dict(seed=g["seed"], game_ids=[g["game_id"]])
+        aliased = execute_episodes(1, g["n"], HashPriorNet(), 1, g["sims"], g["T"], g["e_greedy"], reference_aliasing=True, **kw)[0]
+        snap = execute_episodes(1, g["n"], HashPriorNet(), 1, g["sims"], g["T"], g["e_greedy"], **kw)[0]
+        assert len(aliased) == len(snap) == g["n_examples"]
+        assert examples_digest(aliased) == g["sha256_reference_stream"]
+        assert examples_digest(snap) == g["sha256_snapshot_stream"]
+        done += 1
+    assert done >= 4
+
+
+def test_workers_and_runs_never_replay_episodes():
+    """every worker / every WorkerManager.run() used to replay the same e-greedy streams (fixed seed 0, ids
+    0..n-1).  Now ids come from a process-wide allocator and the default seed is drawn per process."""
+    from othellozero_b200.mcts import HashPriorNet
+    from othellozero_b200.selfplay import WorkType, make_b200_worker
+
+    def moves_of(results):
+        return {tuple(int(np.argmax(ex[8 * i + 7][1])) for i in range(len(ex) // 8)) for ex in results}
+
+    w1, w2 = make_b200_worker()(), make_b200_worker()()
+    runs = []
+    for w in (w1, w2, w1):
+        w.run(WorkType.EXECUTE_EPISODE, 6, 6, HashPriorNet(), 1, 8, 1, 0.4)
+        w.wait()
+        res = w.get_results()
+        assert len(res) == 6
+        runs.append(moves_of(res))
+    assert len(runs[0]) >= 5                                   # e_greedy 0.4: episodes of one run differ
+    assert not (runs[0] & runs[1]) and not (runs[0] & runs[2]) and not (runs[1] & runs[2])
+    # an explicit seed + explicit ids stay reproducible
+    from othellozero_b200.selfplay import execute_episodes
+    a = execute_episodes(3, 6, HashPriorNet(), 1, 8, 1, 0.4, seed=5, game_ids=[1, 2, 3])
+    b = execute_episodes(3, 6, HashPriorNet(), 1, 8, 1, 0.4, seed=5, game_ids=[1, 2, 3])
+    assert moves_of(a) == moves_of(b) and len(moves_of(a)) == 3

@@ -286,3 +286,22 @@ def test_game_queue_with_network_matches_one_batch():
         k = int(a["n_moves"][g])
         assert np.array_equal(a["action"][g][:k], b["action"][g][:k])
         assert np.array_equal(a["visits"][g][:k], b["visits"][g][:k])
+
+
+@pytest.mark.parametrize("n", [6, 8])
+def test_device_tower_reproduces_delta_network_known_answer(n, conv2_mode):
+    """The hand-derived whole-network answer of tests/kat_net.py (HWIO cross-correlation, 'same' padding, (h,w,c) flatten,
+    Dense (in,out), BN folding) on the CUDA tower itself - not only through the fp32 restatement."""
+    import kat_net
+    from othellozero_b200 import engine
+    C = 128
+    blob, boards, exp = kat_net.delta_network(n, C, bn5=(2.0, 0.1, 0.5, 4.0 - 1e-3))
+    own = np.array([sum(1 << (r * 8 + c) for r in range(n) for c in range(n) if boards[b, r, c, 0]) for b in range(2)], dtype=np.uint64)
+    opp = np.array([sum(1 << (r * 8 + c) for r in range(n) for c in range(n) if boards[b, r, c, 1]) for b in range(2)], dtype=np.uint64)
+    e = engine.Engine(n, max_games=4, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+    e.load_weights(blob, C)
+    pi, lg, v = e.net_forward(own, opp)
+    e.close()
+    assert np.abs(lg - exp["logits"]).max() <= TOL, np.abs(lg - exp["logits"]).max()
+    assert np.abs(v - exp["v"]).max() <= TOL and np.abs(pi - exp["pi"]).max() <= TOL
+    assert abs(float(lg[0].max() - lg[1].max())) > 1.0      # board 0 hits the fc1 tap, the transposed board 1 misses it

@@ -256,3 +256,96 @@ def test_game_queue_default_ids_and_partial_run(E):
     rt = t.selfplay_records()
     assert (rt["n_moves"] == 5).all() and (rt["winner"] == -1).all()
     t.close()
+
+
+# ---- temperature 0 and the engine RNG (main.py:73-76 switches self-play to T = 0 after `temperature_threshold`) ----------
+def test_selfplay_rng_golden(E, golden_rng_episodes):
+    """Device self-play against the REFERENCE'S OWN execute_episode run with the engine's draws injected
+    (tools/gen_golden.py::EngineRng): T = 0 tie-breaks over the arg-max set, e-greedy coin, random legal action."""
+    groups = {}
+    for rec in golden_rng_episodes:
+        if rec["prior"] == "hash":
+            groups.setdefault((rec["n"], rec["sims"], rec["c"], rec["T"], rec["e_greedy"], rec["seed"]), []).append(rec)
+    assert sum(r["rng_calls"]["ties"] for g in groups.values() for r in g) > 40
+    for (n, sims, c, T, eg, seed), recs in groups.items():
+        ids = [r["game_id"] for r in recs]
+        e = E.Engine(n, max_games=2, nodes_per_game=sims * n * n + 64, prior_mode=E.PRIOR_HASH, c_puct=c, seed=seed)
+        e.selfplay_begin(len(ids), sims, temperature=T, e_greedy=eg, game_ids=ids)   # 2 slots: the others are queued
+        assert e.selfplay_run(-1) == 0
+        out = e.selfplay_records()
+        assert e.counters()["nodes"] == sum(r["net_calls"] for r in recs)
+        e.close()
+        for g, rec in enumerate(recs):
+            k = int(out["n_moves"][g])
+            assert [int(a) for a in out["action"][g][:k]] == [sq8(a, n) for a in rec["moves"]], (n, sims, T, eg, seed, g)
+            z = [1 if int(out["winner"][g]) == int(p) else -1 for p in out["player"][g][:k]]
+            assert z == rec["z"]
+
+
+@pytest.mark.parametrize("n,sims,eg", [(6, 4, 1.0), (6, 25, 1.0), (8, 6, 1.0), (8, 30, 0.85)])
+def test_temperature_zero_vs_oracle(E, n, sims, eg):
+    """T = 0 episodes equal the oracle move for move (positions, movers, per-move visit counts, winner); few simulations
+    per move make ties in the arg-max set frequent, so the tie-break draw is exercised on most moves."""
+    G, slots = 24, 8
+    starts = [oracle.playout(n, 9, g, max_moves=g % 4) for g in range(G)]
+    black = [s["black"] for s in starts]; white = [s["white"] for s in starts]; player = [s["player"] for s in starts]
+    ids = [5000 + 3 * g for g in range(G)]
+    e = E.Engine(n, slots, sims * n * n + 64, E.PRIOR_HASH, seed=77, log_visits=True)
+    e.selfplay_begin(G, sims, 0.0, eg, -1, black, white, player, ids)
+    assert e.selfplay_run(-1) == 0
+    out = e.selfplay_records()
+    e.close()
+    tie_moves = 0
+    for g in range(G):
+        ref = oracle.execute_episode(n, sims, temperature=0.0, e_greedy=eg, seed=77, game_id=ids[g],
+                                     start_board=starts[g]["board"], start_player=player[g], log_visits=True)
+        k = int(out["n_moves"][g])
+        assert [int(a) for a in out["action"][g][:k]] == [sq8(a, n) for a in ref["moves"]], f"game {g}"
+        assert [int(p) for p in out["player"][g][:k]] == ref["players"]
+        assert [int(x) for x in out["black"][g][:k]] == ref["black"] and [int(x) for x in out["white"][g][:k]] == ref["white"]
+        assert int(out["winner"][g]) == ref["winner"]
+        for p in range(k):
+            v = visits_to_grid(out["visits"][g][p], n)
+            assert v.tolist() == ref["visits"][p].tolist()
+            tie_moves += int((v == v.max()).sum() > 1)
+    assert tie_moves > (20 if sims <= 6 else 0)
+
+
+def test_final_position_is_recorded(E):
+    """Entry n_moves of a game's position row = the position the episode ended in (include/oz_b200.h)."""
+    n, sims, G = 6, 8, 12
+    e = E.Engine(n, 4, sims * 36 + 64, E.PRIOR_HASH, seed=3)
+    e.selfplay_begin(G, sims, 1.0, 0.9)
+    assert e.selfplay_run(-1) == 0
+    rec = e.selfplay_records()
+    e.close()
+    for g in range(G):
+        k = int(rec["n_moves"][g])
+        pl = int(rec["player"][g][k - 1])
+        b, w = int(rec["black"][g][k - 1]), int(rec["white"][g][k - 1])
+        own, opp = (w, b) if pl else (b, w)
+        o2, p2, fl, _ = E.apply_moves([own], [opp], [int(rec["action"][g][k - 1])], n)
+        assert int(fl[0]) & 4
+        fb, fw = (int(p2[0]), int(o2[0])) if pl else (int(o2[0]), int(p2[0]))
+        assert (int(rec["black"][g][k]), int(rec["white"][g][k])) == (fb, fw)
+
+
+def test_seed_and_game_id_do_not_commute(E):
+    """(seed 1, id g) used to replay (seed 0, id g ^ 1): stream keys now mix seed and id non-commutatively."""
+    n, sims, G = 6, 6, 16
+
+    def play(seed, ids):
+        e = E.Engine(n, G, sims * 36 + 64, E.PRIOR_HASH, seed=seed)
+        e.selfplay_begin(G, sims, 1.0, 0.3, game_ids=ids)
+        assert e.selfplay_run(-1) == 0
+        r = e.selfplay_records()
+        e.close()
+        return {int(i): bytes(r["action"][g]) for g, i in enumerate(ids)}
+
+    a = play(0, list(range(G)))
+    b = play(1, list(range(G)))
+    assert len(set(a.values())) > G // 2                       # e_greedy 0.3: games differ from each other
+    assert sum(a[g] == b[g ^ 1] for g in range(G)) <= 1        # ... and seed 1 is not a permutation of seed 0
+    assert len(set(a.values()) & set(b.values())) <= 1
+    c = play(0, list(range(G)))
+    assert a == c                                              # same (seed, ids) -> same games

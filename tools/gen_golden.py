@@ -264,7 +264,8 @@ def gen_examples():
     true per-move snapshots (boards rebuilt from the moves)."""
     out = []
     for n, sims, prior_name, T, eg, seed, gid in ((6, 25, "hash", 1, 1.0, 0, 0), (6, 25, "sha", 0, 0.7, 3, 5),
-                                                   (8, 100, "hash", 1, 1.0, 0, 0), (4, 30, "sha", 1, 0.5, 9, 2)):
+                                                   (8, 100, "hash", 1, 1.0, 0, 0), (4, 30, "sha", 1, 0.5, 9, 2),
+                                                   (6, 6, "hash", 0, 0.8, 21, 4), (8, 8, "hash", 0, 0.9, 22, 7)):
         prior = {"hash": hash_prior, "sha": prior_fns.sha_prior}[prior_name]
         ex, rng, net = reference_episode_with_engine_rng(n, sims, prior, 1, T, eg, seed, gid)
         k = len(ex) // 8
