@@ -82,18 +82,40 @@ def _mode_for(net):
     raise TypeError("pit() needs B200NNet / HashPriorNet agents (or RANDOM_AGENT)")
 
 
-def _kth_set_bit(mask: int, k: int) -> int:
-    for _ in range(k):
-        mask &= mask - 1
-    return (mask & -mask).bit_length() - 1
+def _popcount(x: np.ndarray) -> np.ndarray:
+    return np.unpackbits(np.ascontiguousarray(x, dtype="<u8").view(np.uint8).reshape(-1, 8), axis=1).sum(axis=1).astype(np.int64)
+
+
+def _kth_set_bits(masks: np.ndarray, k: np.ndarray) -> np.ndarray:
+    """Square (bit index) of the k[i]-th set bit of masks[i], ascending = row-major; all games at once."""
+    bits = np.unpackbits(np.ascontiguousarray(masks, dtype="<u8").view(np.uint8).reshape(-1, 8), axis=1,
+                         bitorder="little").astype(bool)                       # [G, 64], column = square bit
+    rank = np.cumsum(bits, axis=1) - 1
+    return np.argmax(bits & (rank == np.asarray(k, dtype=np.int64)[:, None]), axis=1).astype(np.int32)
+
+
+def _draw_indices(rng, counts: np.ndarray) -> np.ndarray:
+    """One uniform index in [0, counts[i]) per game.  A numpy Generator draws them all at once; any other rng (Python's
+    ``random`` by default, as in the reference: agents.py:22-23, othelo_mcts.py:58-59) is asked once per game that
+    really has a choice, with the reference's call form ``rng.choice(sequence)``."""
+    counts = np.asarray(counts, dtype=np.int64)
+    if hasattr(rng, "integers"):
+        return rng.integers(0, counts)
+    out = np.zeros(counts.shape[0], dtype=np.int64)
+    for i in np.nonzero(counts > 1)[0]:
+        out[i] = rng.choice(range(int(counts[i])))
+    return out
 
 
 def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1, n_games=64, device=0, rng=None,
         start_black=None, start_white=None, start_player=None):
     """n_games simultaneous duels, net_black playing BLACK.  Returns dict(winner [n_games] 0/1, black, white, plies).
-    Ties in the visit counts are broken with ``rng.choice`` (default: Python's ``random``) like the reference.
-    Either side may be ``RANDOM_AGENT``: it plays ``rng.choice`` over its legal moves in row-major order
-    (RandomOthelloAgent, agents.py:20-24; main.py:165-197 evaluates the network against it)."""
+    Every step is one kernel chain over all games whose turn it is: one search launch per network side
+    (NeuralNetworkOthelloAgent.play, agents.py:52-68, always temperature 0), one move-generator launch for a
+    ``RANDOM_AGENT`` side (RandomOthelloAgent.play, agents.py:20-24; main.py:165-197 evaluates the network against it),
+    one rules launch to apply the moves.  Ties in the visit counts and the random agent's moves are drawn from ``rng``
+    (Python's ``random`` like the reference, or a numpy Generator for fully vectorised draws) over the candidates in
+    row-major order."""
     rng = rng or random
     n = board_size
     nodes = num_simulations * (n * n) + 64
@@ -109,9 +131,8 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
             e.load_weights(net.blob, net.channels)
         engines.append(e)
     if start_black is None:
-        b0, w0 = OthelloGame.initial_board(n), None
         from .othello import _bits
-        bb, ww = _bits(b0)
+        bb, ww = _bits(OthelloGame.initial_board(n))
         black = np.full(n_games, bb, dtype=np.uint64)
         white = np.full(n_games, ww, dtype=np.uint64)
         player = np.zeros(n_games, dtype=np.int32)
@@ -131,29 +152,20 @@ def pit(board_size, net_black, net_white, num_simulations, degree_exploration=1,
                 if not turn.any():
                     continue
                 idx = np.nonzero(turn)[0]
+                own = np.where(player[idx] == 0, black[idx], white[idx])
+                opp = np.where(player[idx] == 0, white[idx], black[idx])
                 if e is None:  # the random agent: uniform over the legal moves (GPU move generator, host RNG)
-                    own = np.where(player[idx] == 0, black[idx], white[idx])
-                    opp = np.where(player[idx] == 0, white[idx], black[idx])
                     legal = _e.legal_moves(own, opp, n, device)
-                    sq = np.zeros(idx.size, dtype=np.int32)
-                    for j, m in enumerate(legal):
-                        m = int(m)
-                        sq[j] = _kth_set_bit(m, rng.choice(range(bin(m).count("1"))))
+                    sq = _kth_set_bits(legal, _draw_indices(rng, _popcount(legal)))
                 else:
                     # games where it is not this agent's turn get a root with no legal move for the mover: the
                     # kernel skips them (0 simulations), exactly like an agent that is not asked to play
-                    rb = np.where(turn, black, 0).astype(np.uint64)
-                    rw = np.where(turn, white, 0).astype(np.uint64)
-                    e.set_roots(rb, rw, player)
+                    e.set_roots(np.where(turn, black, 0).astype(np.uint64), np.where(turn, white, 0).astype(np.uint64), player)
                     e.search(num_simulations)
-                    visits, _ = e.visits()
-                    sq = np.zeros(idx.size, dtype=np.int32)
-                    for j, g in enumerate(idx):
-                        v = visits[g]
-                        bests = np.nonzero(v == v.max())[0]
-                        sq[j] = int(bests[0]) if bests.size == 1 else int(rng.choice(list(bests)))
-                own = np.where(player[idx] == 0, black[idx], white[idx])
-                opp = np.where(player[idx] == 0, white[idx], black[idx])
+                    visits = e.visits()[0][idx]                                    # [games to move, 64] by square bit
+                    tied = visits == visits.max(axis=1, keepdims=True)             # othelo_mcts.py:58: the arg-max set
+                    pick = _draw_indices(rng, tied.sum(axis=1))                    # a unique maximum needs no draw
+                    sq = np.argmax(tied & ((np.cumsum(tied, axis=1) - 1) == pick[:, None]), axis=1).astype(np.int32)
                 o2, p2, fl, _ = _e.apply_moves(own, opp, sq, n, device)
                 assert not (fl & 0x80000000).any()
                 swapped = (fl & 1).astype(bool)

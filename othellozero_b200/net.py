@@ -158,29 +158,26 @@ def init_weights(board_size: int, channels: int = 512, seed: int = 0, randomize_
     return pack_blob(w, board_size, channels)
 
 
+_SQUARE_BIT = (np.uint64(1) << (np.arange(8, dtype=np.uint64)[:, None] * np.uint64(8) + np.arange(8, dtype=np.uint64)[None, :]))
+
+
 def boards_to_bits(boards) -> tuple[np.ndarray, np.ndarray]:
     """(B,N,N,2) bool/0-1 array -> (ch0 bits, ch1 bits) uint64, bit r*8+c."""
     b = np.asarray(boards).astype(bool)
     if b.ndim == 3:
         b = b[None]
-    B, n = b.shape[0], b.shape[1]
-    weights = np.zeros((n, n), dtype=np.uint64)
-    for r in range(n):
-        for c in range(n):
-            weights[r, c] = np.uint64(1) << np.uint64(r * 8 + c)
-    own = (b[..., 0] * weights).sum(axis=(1, 2), dtype=np.uint64)
-    opp = (b[..., 1] * weights).sum(axis=(1, 2), dtype=np.uint64)
+    n = b.shape[1]
+    w = _SQUARE_BIT[:n, :n]
+    own = (b[..., 0] * w).sum(axis=(1, 2), dtype=np.uint64)
+    opp = (b[..., 1] * w).sum(axis=(1, 2), dtype=np.uint64)
     return own, opp
 
 
 def bits_to_board(ch0: int, ch1: int, n: int) -> np.ndarray:
     """-> (N,N,2) bool array in the reference's layout (Othello/__init__.py:22-25)."""
-    out = np.zeros((n, n, 2), dtype=bool)
-    for r in range(n):
-        for c in range(n):
-            out[r, c, 0] = (int(ch0) >> (r * 8 + c)) & 1
-            out[r, c, 1] = (int(ch1) >> (r * 8 + c)) & 1
-    return out
+    words = np.array([int(ch0), int(ch1)], dtype="<u8").view(np.uint8).reshape(2, 8)     # byte r of a word = row r
+    planes = np.unpackbits(words, axis=1, bitorder="little").reshape(2, 8, 8)[:, :n, :n]
+    return np.ascontiguousarray(np.moveaxis(planes, 0, -1)).astype(bool)
 
 
 class B200NNet:

@@ -3,8 +3,11 @@ rule evaluated by the CUDA bitboard kernels (K1/K2) through the C-ABI.
 
 Same names, argument meaning and error behaviour as the reference so that training.py / agents.py /
 othelo_mcts.py keep working when they import ``OthelloGame`` from here.  Boards are the reference's
-``(N,N,2)`` bool arrays (channel 0 = BLACK, 1 = WHITE); each call converts to two uint64 bitboards and
-launches a kernel — convenient, not fast.  The fast path is the batched engine (selfplay.py).
+``(N,N,2)`` bool arrays (channel 0 = BLACK, 1 = WHITE); each call converts to two uint64 bitboards (vectorised)
+and launches a kernel for ONE position — the interface the reference's per-game callers expect.  Many positions at once
+go through engine.legal_moves / apply_moves / score (arena.pit) or the batched engine (selfplay.py).  The reference's
+ray generators (get_direction_squares / get_all_directions_squares, :186-198) have no counterpart: rays are shift masks
+inside the kernels (csrc/oz_bitboard.cuh).
 
 Deliberate deviations are listed in INTEGRATION.md (e.g. ``is_square_free`` works here; the reference's
 version raises NameError, Othello/__init__.py:88-98).
@@ -34,40 +37,46 @@ class OthelloPlayer(Enum):
         return OthelloPlayer.WHITE if self is OthelloPlayer.BLACK else OthelloPlayer.BLACK
 
 
+_SQUARE_BIT = (np.uint64(1) << (np.arange(8, dtype=np.uint64)[:, None] * np.uint64(8) + np.arange(8, dtype=np.uint64)[None, :]))
+
+
 def _bits(board) -> tuple[int, int]:
-    b = np.asarray(board)
+    """(N,N,2) board -> (channel 0 bits, channel 1 bits), bit r*8+c; one masked sum per channel, no Python loop."""
+    b = np.asarray(board).astype(bool)
     n = b.shape[0]
-    black = white = 0
-    rr, cc = np.nonzero(b[..., 0])
-    for r, c in zip(rr, cc):
-        black |= 1 << (int(r) * 8 + int(c))
-    rr, cc = np.nonzero(b[..., 1])
-    for r, c in zip(rr, cc):
-        white |= 1 << (int(r) * 8 + int(c))
-    return black, white
+    w = _SQUARE_BIT[:n, :n]
+    return int(w[b[..., 0]].sum(dtype=np.uint64)), int(w[b[..., 1]].sum(dtype=np.uint64))
+
+
+def _planes(bits: int, n: int) -> np.ndarray:
+    """uint64 -> (N,N) bool plane (byte r of the little-endian word = row r)."""
+    rows = np.frombuffer(int(bits).to_bytes(8, "little"), dtype=np.uint8)
+    return np.unpackbits(rows[:, None], axis=1, bitorder="little")[:n, :n].astype(bool)
 
 
 def _mask_to_squares(mask: int, n: int):
-    return [(s >> 3, s & 7) for s in range(64) if (mask >> s) & 1 and (s >> 3) < n and (s & 7) < n]
+    rr, cc = np.nonzero(_planes(mask, n))           # row-major, like np.argwhere in the reference (:200-210)
+    return list(zip(rr.tolist(), cc.tolist()))
 
 
 class OthelloGame:
     PLAYER_CHANNELS = {OthelloPlayer.BLACK: 0, OthelloPlayer.WHITE: 1}
-    ALL_DIRECTIONS = np.array([(1, 1), (1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1), (0, 1)])
     device = 0  # CUDA ordinal used by the static rule calls
 
     def __init__(self, board_size=8, initial_board=None, current_player=OthelloPlayer.BLACK):
-        """Othello/__init__.py:29-59."""
+        """Othello/__init__.py:29-59: same arguments, same assertions; a supplied board is adopted (not copied)."""
         assert board_size % 2 == 0, 'Board size must be even'
-        assert initial_board is None or initial_board.shape == (board_size, board_size, 2), \
-            f'Expecting initial board shape ({board_size}, {board_size}, 2)'
-        self._board = initial_board if initial_board is not None else self.initial_board(board_size)
-        self._board_size = board_size
-        self._round = 1
+        if initial_board is None:
+            initial_board = self.initial_board(board_size)
+            finished = False
+        else:
+            assert initial_board.shape == (board_size, board_size, 2), \
+                f'Expecting initial board shape ({board_size}, {board_size}, 2)'
+            finished = OthelloGame.has_board_finished(initial_board)
+        self._board, self._board_size, self._round = initial_board, board_size, 1
         self.current_player = current_player
-        self._one_channel_board_last_update = None
-        self._one_channel_board = None
-        self._has_finished = OthelloGame.has_board_finished(self._board) if initial_board is not None else False
+        self._has_finished = finished
+        self._one_channel_cache = (None, None)   # (round it was built in, array)
 
     # ---- instance API (Othello/__init__.py:61-175) ----------------------------------------------
     @property
@@ -79,14 +88,15 @@ class OthelloGame:
         return self._round
 
     def board(self, view=BoardView.ONE_CHANNEL):
-        if view == BoardView.TWO_CHANNELS:
-            return self._board  # the live array, as in the reference (:77-78)
-        elif view == BoardView.ONE_CHANNEL:
-            if self._one_channel_board_last_update != self.round:
-                self._one_channel_board = OthelloGame.convert_to_one_channel_board(self._board)
-                self._one_channel_board_last_update = self.round
-            return self._one_channel_board
-        raise TypeError('Expecting BoardView type')
+        """:77-86 - TWO_CHANNELS hands out the LIVE array (callers alias it); ONE_CHANNEL is rebuilt once
+        per round."""
+        if not isinstance(view, BoardView):
+            raise TypeError('Expecting BoardView type')
+        if view is BoardView.TWO_CHANNELS:
+            return self._board
+        if self._one_channel_cache[0] != self._round:
+            self._one_channel_cache = (self._round, OthelloGame.convert_to_one_channel_board(self._board))
+        return self._one_channel_cache[1]
 
     def is_square_free(self, row, col):
         return OthelloGame.is_board_square_free(self._board, row, col)
@@ -137,10 +147,8 @@ class OthelloGame:
 
     def _write_bits(self, black, white):
         n = self._board_size
-        for r in range(n):
-            for c in range(n):
-                self._board[r, c, 0] = (black >> (r * 8 + c)) & 1
-                self._board[r, c, 1] = (white >> (r * 8 + c)) & 1
+        self._board[..., 0] = _planes(black, n)     # in place: the array is shared with whoever holds board(TWO_CHANNELS)
+        self._board[..., 1] = _planes(white, n)
 
     def get_players_points(self):
         return OthelloGame.get_board_players_points(self._board)
@@ -151,24 +159,13 @@ class OthelloGame:
     # ---- static array API (Othello/__init__.py:177-274) -----------------------------------------
     @staticmethod
     def initial_board(board_size):
+        """:177-184 - WHITE on the main diagonal of the centre 2x2, BLACK on the other two squares."""
         assert board_size % 2 == 0, 'Board size must be even'
-        initial = np.array([[[0, 1], [1, 0]], [[1, 0], [0, 1]]], dtype=bool)
-        pad = (board_size - 2) // 2
-        return np.pad(initial, ((pad, pad), (pad, pad), (0, 0)), constant_values=0)
-
-    @staticmethod
-    def get_all_directions_squares(board_size, row, col):
-        for direction in OthelloGame.ALL_DIRECTIONS:
-            yield OthelloGame.get_direction_squares(board_size, direction, row, col)
-
-    @staticmethod
-    def get_direction_squares(board_size, direction, row, col):
-        row_offset, col_offset = direction
-        row, col = row + row_offset, col + col_offset
-        while 0 <= row < board_size and 0 <= col < board_size:
-            yield row, col
-            row += row_offset
-            col += col_offset
+        board = np.zeros((board_size, board_size, 2), dtype=bool)
+        lo, hi = board_size // 2 - 1, board_size // 2
+        board[[lo, hi], [lo, hi], 1] = True
+        board[[lo, hi], [hi, lo], 0] = True
+        return board
 
     @staticmethod
     def get_board_free_squares(board):
@@ -219,14 +216,12 @@ class OthelloGame:
 
     @staticmethod
     def flip_board_squares(board, player, row, col):
-        """In place, like the reference (:237-247)."""
-        player_channel = OthelloGame.PLAYER_CHANNELS[player]
-        opponent_channel = OthelloGame.PLAYER_CHANNELS[player.opponent]
-        for flip_row, flip_col in OthelloGame.get_action_flip_squares(board, player, row, col):
-            board[flip_row, flip_col, player_channel] = 1
-            board[flip_row, flip_col, opponent_channel] = 0
-        board[row, col, player_channel] = 1
-        board[row, col, opponent_channel] = 0
+        """:237-247, in place: the flipped squares and the played square go to `player`'s channel."""
+        mine = OthelloGame.PLAYER_CHANNELS[player]
+        squares = list(OthelloGame.get_action_flip_squares(board, player, row, col)) + [(row, col)]
+        rr, cc = zip(*squares)
+        board[rr, cc, mine] = True
+        board[rr, cc, 1 - mine] = False
 
     @staticmethod
     def has_board_finished(board):
@@ -249,9 +244,9 @@ class OthelloGame:
 
     @staticmethod
     def convert_to_one_channel_board(board):
-        one_channel = board[:, :, 0] * OthelloPlayer.BLACK.value
-        one_channel = one_channel + board[:, :, 1] * OthelloPlayer.WHITE.value
-        return one_channel
+        """:266-270 - +1 where BLACK, -1 where WHITE (the players' enum values), 0 elsewhere."""
+        b = np.asarray(board)
+        return b[..., 0] * OthelloPlayer.BLACK.value + b[..., 1] * OthelloPlayer.WHITE.value
 
     @staticmethod
     def invert_board(board):

@@ -109,6 +109,27 @@ def bits_to_boards(black, white, board_size: int) -> np.ndarray:
     return np.stack([planes(black), planes(white)], axis=-1).astype(bool)
 
 
+def expand_symmetries(black, white, action, board_size: int):
+    """Positions [P] (bitboards + action square bit) -> (boards (P,8,N,N,2) bool, one-hot policies (P,8,N,N) float64):
+    the 8 symmetric copies of training.py:13-23, in its order, for every position at once."""
+    n = board_size
+    boards = bits_to_boards(black, white, n)
+    action = np.asarray(action).astype(np.int64)
+    P = boards.shape[0]
+    b8 = np.empty((P, 8, n, n, 2), dtype=bool)
+    p8 = np.zeros((P, 8, n, n))                  # one-hot policies: set the image of the action square under each symmetry
+    rows, ar, ac = np.arange(P), action >> 3, action & 7
+    s = 0
+    for quarter_turns in (1, 2, 3, 4):
+        rb = np.rot90(boards, k=quarter_turns, axes=(1, 2))
+        ar, ac = n - 1 - ac, ar                                                          # np.rot90: out[i, j] = in[j, n-1-i]
+        for mirrored in (True, False):                                                   # the mirrored copy comes first
+            b8[:, s] = rb[:, :, ::-1] if mirrored else rb                                # np.fliplr of one (N,N,.) board
+            p8[rows, s, ar, (n - 1 - ac) if mirrored else ac] = 1
+            s += 1
+    return b8, p8
+
+
 def records_to_examples_batch(rec: dict, board_size: int, games=None):
     """All games' records -> per-game example lists (training.py:58-72 + the 8 symmetries of :13-23), built with array
     operations over every (game, ply) at once: ~40x faster than calling records_to_examples per game (45 s -> ~1 s per
@@ -119,20 +140,9 @@ def records_to_examples_batch(rec: dict, board_size: int, games=None):
     gsel = np.repeat(np.asarray(list(games), dtype=np.int64), nm)                        # game of every (game, ply) row
     psel = np.concatenate([np.arange(k) for k in nm]) if len(nm) else np.zeros(0, dtype=np.int64)
     P = int(gsel.size)
-    boards = bits_to_boards(np.asarray(rec["black"])[gsel, psel], np.asarray(rec["white"])[gsel, psel], n)
-    action = np.asarray(rec["action"])[gsel, psel].astype(np.int64)
+    b8, p8 = expand_symmetries(np.asarray(rec["black"])[gsel, psel], np.asarray(rec["white"])[gsel, psel],
+                               np.asarray(rec["action"])[gsel, psel], n)
     z = np.where(np.asarray(rec["winner"])[gsel] == np.asarray(rec["player"])[gsel, psel], 1, -1)
-    b8 = np.empty((P, 8, n, n, 2), dtype=bool)
-    p8 = np.zeros((P, 8, n, n))                  # one-hot policies: set the image of the action square under each symmetry
-    rows, ar, ac = np.arange(P), action >> 3, action & 7
-    s = 0
-    for rotation in range(1, 5):                                                         # training.py:16-22 order
-        rb = np.rot90(boards, k=rotation, axes=(1, 2))
-        ar, ac = n - 1 - ac, ar                                                          # np.rot90: out[i, j] = in[j, n-1-i]
-        for flip in (True, False):
-            b8[:, s] = rb[:, :, ::-1] if flip else rb                                    # np.fliplr of one (N,N,.) board
-            p8[rows, s, ar, (n - 1 - ac) if flip else ac] = 1
-            s += 1
     # one (board view, policy view, z) tuple per example, made by C-level iteration over the leading axis
     flat = list(zip(b8.reshape(P * 8, n, n, 2), p8.reshape(P * 8, n, n), np.repeat(np.asarray(z, dtype=np.int64), 8).tolist()))
     out, row = [], 0

@@ -1,10 +1,21 @@
 """Training step ("next" row): NNetWrapper.train (Net/NNet.py:53-68) with the compile settings of
-Net/OthelloNN.py:55-56 — categorical cross-entropy on the policy + MSE on the value, Adam(lr, clipvalue=0.5),
-dropout 0.3, BatchNormalization momentum 0.99 / eps 1e-3, batch 32, 10 epochs — done by PyTorch autograd.
+Net/OthelloNN.py:55-56 - Adam(lr, clipvalue=0.5), dropout 0.3, BatchNormalization momentum 0.99 / eps 1e-3, batch 32,
+10 epochs - done by PyTorch autograd.
 
 This is host-side plumbing around the hot path, not a hand-written kernel: the self-play engine consumes the result
 as a weight blob (oz_net_load_weights* folds BN and casts to bf16 on the device).
-"""
+
+Two details of what Keras actually computes, reproduced here (both were deviations in round 1):
+  * the policy loss.  compile() names 'categorical_crossentropy' for the output 'pi-reshaped' of shape (B,N,N)
+    (Net/OthelloNN.py:51,55), and Keras applies that loss along the LAST axis: every board ROW is renormalised and scored
+    as its own distribution, then averaged over B*N rows.  With one-hot targets only the target's row contributes, so the
+    loss is (1/N) * -log(pi[r*,c*] / sum_c pi[r*,c]) - not a cross-entropy over the N*N squares.  `policy_loss=
+    "reference"` (default) is that; "full_board" is the textbook -log pi[r*,c*].
+  * BatchNormalization's moving_variance is updated with the BIASED batch variance (torch's BatchNorm uses the unbiased
+    one for running_var): KerasBatchNorm below.
+Multi-GPU: `train_blob(..., ddp=True)` under torch.distributed shards every global batch over the ranks (rank r takes
+samples r::world), synchronises the BatchNormalization batch statistics and averages the gradients, so N GPUs take the
+SAME optimisation steps one GPU would (tests/test_train_cpu.py, gloo world 2)."""
 from __future__ import annotations
 
 import numpy as np
@@ -14,8 +25,47 @@ import torch.nn.functional as F
 
 from .net import blob_layout, pack_blob, unpack_blob
 
-BN_EPS = 1e-3       # keras BatchNormalization default
-BN_MOMENTUM = 0.01  # torch convention = 1 - keras momentum (0.99)
+BN_EPS = 1e-3          # keras BatchNormalization default
+KERAS_MOMENTUM = 0.99  # moving = 0.99 * moving + 0.01 * batch
+KERAS_CE_EPS = 1e-7    # keras.backend.epsilon(): categorical_crossentropy clips probabilities to [eps, 1 - eps]
+
+
+def _dist_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class KerasBatchNorm(nn.Module):
+    """keras.layers.BatchNormalization over dimension 1 (channels of NCHW / features): training normalises with the
+    batch mean and BIASED variance and moves the moving statistics with them (momentum 0.99); inference uses the moving
+    statistics.  sync=True pools the batch statistics over all ranks (differentiably)."""
+
+    def __init__(self, features: int, eps: float = BN_EPS, momentum: float = KERAS_MOMENTUM):
+        super().__init__()
+        self.eps, self.momentum, self.sync = eps, momentum, False
+        self.weight = nn.Parameter(torch.ones(features))
+        self.bias = nn.Parameter(torch.zeros(features))
+        self.register_buffer("running_mean", torch.zeros(features))
+        self.register_buffer("running_var", torch.ones(features))
+
+    def forward(self, x):
+        shape = [1, -1] + [1] * (x.dim() - 2)
+        if self.training:
+            dims = [0] + list(range(2, x.dim()))
+            count = x.numel() // x.shape[1]
+            s1, s2 = x.sum(dims), (x * x).sum(dims)
+            if self.sync and _dist_world() > 1:
+                import torch.distributed.nn.functional as dfn
+                packed = dfn.all_reduce(torch.cat([s1, s2, s1.new_tensor([float(count)])]))
+                s1, s2, count = packed[:s1.numel()], packed[s1.numel():-1], packed[-1]
+            mean = s1 / count
+            var = (s2 / count - mean * mean).clamp_min(0.0)
+            with torch.no_grad():
+                self.running_mean.mul_(self.momentum).add_(mean.detach(), alpha=1 - self.momentum)
+                self.running_var.mul_(self.momentum).add_(var.detach(), alpha=1 - self.momentum)
+        else:
+            mean, var = self.running_mean, self.running_var
+        return (x - mean.view(shape)) * torch.rsqrt(var.view(shape) + self.eps) * self.weight.view(shape) + self.bias.view(shape)
 
 
 class OthelloNNTorch(nn.Module):
@@ -27,11 +77,10 @@ class OthelloNNTorch(nn.Module):
         self.n, self.C = n, C
         self.convs = nn.ModuleList([nn.Conv2d(2, C, 3, padding=1), nn.Conv2d(C, C, 3, padding=1),
                                     nn.Conv2d(C, C, 3), nn.Conv2d(C, C, 3)])
-        self.bns = nn.ModuleList([nn.BatchNorm2d(C, eps=BN_EPS, momentum=BN_MOMENTUM) for _ in range(4)])
+        self.bns = nn.ModuleList([KerasBatchNorm(C) for _ in range(4)])
         k1 = (n - 4) * (n - 4) * C
         self.fc1, self.fc2 = nn.Linear(k1, 1024), nn.Linear(1024, 512)
-        self.bn5 = nn.BatchNorm1d(1024, eps=BN_EPS, momentum=BN_MOMENTUM)
-        self.bn6 = nn.BatchNorm1d(512, eps=BN_EPS, momentum=BN_MOMENTUM)
+        self.bn5, self.bn6 = KerasBatchNorm(1024), KerasBatchNorm(512)
         self.pi, self.v = nn.Linear(512, n * n), nn.Linear(512, 1)
         self.dropout = dropout
 
@@ -98,18 +147,42 @@ def examples_to_arrays(examples):
     return boards, pis, vs
 
 
+def policy_loss_per_sample(logits, target, n: int, kind: str = "reference"):
+    """Per-sample policy loss.  "reference": what Keras computes for the (B,N,N) 'pi-reshaped' output
+    (Net/OthelloNN.py:51,55; see the module docstring) - row-wise renormalised, clipped cross-entropy, averaged over the
+    N rows.  "full_board": cross-entropy over all N*N squares."""
+    if kind == "full_board":
+        return -(target * F.log_softmax(logits, dim=1)).sum(dim=1)
+    pi = torch.softmax(logits, dim=1).view(-1, n, n)
+    rows = pi / pi.sum(dim=2, keepdim=True)
+    rows = rows.clamp(KERAS_CE_EPS, 1.0 - KERAS_CE_EPS)
+    return -(target.view(-1, n, n) * rows.log()).sum(dim=2).mean(dim=1)
+
+
 def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int = 10, batch_size: int = 32,
                lr: float = 1e-3, dropout: float = 0.3, clipvalue: float = 0.5, device=None, seed: int = 0,
-               verbose: bool = False):
-    """model.fit of Net/NNet.py:67-68.  Returns (new_blob, history) with history = per-epoch mean (loss, pi_loss, v_loss)."""
+               verbose: bool = False, policy_loss: str = "reference", ddp: bool = False):
+    """model.fit of Net/NNet.py:67-68.  Returns (new_blob, history) with history = per-epoch mean (loss, pi_loss, v_loss).
+    `examples`: the reference's list of (board, policy, z), or a tuple of arrays (boards (E,N,N,2), policies (E,N*N), z (E,)).
+    ddp=True (inside an initialised torch.distributed group): every rank holds the same examples and the same weights;
+    each global batch of `batch_size` is split over the ranks, BatchNormalization statistics and gradients are pooled,
+    and every rank returns the same new blob."""
+    import torch.distributed as dist
+    world = _dist_world() if ddp else 1
+    rank = dist.get_rank() if world > 1 else 0
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
-    torch.manual_seed(seed)
+    torch.manual_seed(seed + 7919 * rank)          # dropout masks differ per rank, the weights start equal
     model = OthelloNNTorch(board_size, channels, dropout).load_blob(blob).to(device)
-    boards, pis, vs = examples_to_arrays(examples)
-    xb, pb, vb = (torch.from_numpy(a).to(device) for a in (boards, pis, vs))
-    opt = torch.optim.Adam(model.parameters(), lr=lr, eps=1e-7)  # keras Adam epsilon
+    if world > 1:
+        for m in model.modules():
+            if isinstance(m, KerasBatchNorm):
+                m.sync = True
+    boards, pis, vs = examples if isinstance(examples, tuple) else examples_to_arrays(examples)
+    xb, pb, vb = (torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device) for a in (boards, pis, vs))
+    params = [p for p in model.parameters()]
+    opt = torch.optim.Adam(params, lr=lr, eps=1e-7)  # keras Adam epsilon
     n = xb.shape[0]
-    gen = torch.Generator(device="cpu").manual_seed(seed)
+    gen = torch.Generator(device="cpu").manual_seed(seed)   # the same shuffles on every rank
     history = []
     model.train()
     for ep in range(epochs):
@@ -117,21 +190,32 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
         tot = torch.zeros(3, dtype=torch.float64, device=device)  # summed on the device: no host sync per step
         cnt = 0
         for i in range(0, n, batch_size):
-            idx = perm[i:i + batch_size]
-            if idx.numel() < 2:
+            gidx = perm[i:i + batch_size]
+            if gidx.numel() < 2:
                 continue  # BatchNorm needs more than one sample
+            idx = gidx[rank::world]
             logits, v = model(xb[idx])
-            pi_loss = -(pb[idx] * F.log_softmax(logits, dim=1)).sum(dim=1).mean()  # categorical_crossentropy
-            v_loss = F.mse_loss(v, vb[idx])
+            # sums over this rank's samples / the GLOBAL batch size: adding the ranks' gradients gives the batch mean's
+            pi_loss = policy_loss_per_sample(logits, pb[idx], board_size, policy_loss).sum() / gidx.numel()
+            v_loss = ((v - vb[idx]) ** 2).sum() / gidx.numel()
             loss = pi_loss + v_loss
             opt.zero_grad(set_to_none=True)
             loss.backward()
-            torch.nn.utils.clip_grad_value_(model.parameters(), clipvalue)      # Adam(clipvalue=0.5)
+            part = torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double()
+            if world > 1:
+                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+                dist.all_reduce(flat)
+                dist.all_reduce(part)
+                off = 0
+                for p in params:
+                    p.grad = flat[off:off + p.numel()].view_as(p).clone()
+                    off += p.numel()
+            torch.nn.utils.clip_grad_value_(params, clipvalue)      # Adam(clipvalue=0.5)
             opt.step()
-            tot += torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double() * idx.numel()
-            cnt += idx.numel()
+            tot += part * gidx.numel()
+            cnt += gidx.numel()
         history.append(tuple(float(x) for x in (tot / max(1, cnt)).cpu()))
-        if verbose:
+        if verbose and rank == 0:
             print(f"epoch {ep + 1}/{epochs}: loss {history[-1][0]:.4f} pi {history[-1][1]:.4f} v {history[-1][2]:.4f}")
     model.eval()
     return model.cpu().to_blob(), history

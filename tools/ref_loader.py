@@ -59,3 +59,38 @@ class StubNet:
     def predict(self, board):
         self.calls += 1
         return self._fn(board)
+
+
+def _stub_module(name, **attrs):
+    m = types.ModuleType(name)
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    sys.modules[name] = m
+    return m
+
+
+def load_workers():
+    """The reference's workers.py (Worker / ThreadWorker / WorkerManager / WorkType) with its cloud-only imports
+    stubbed: humanfriendly, gcloud (googleapiclient + ssh plumbing) and pickle_training (the remote entry point)."""
+    load()
+    if "workers" not in sys.modules:
+        def _cloud_only(*a, **k):
+            raise RuntimeError("GCE plumbing is not available in the test harness")
+        if "humanfriendly" not in sys.modules:
+            _stub_module("humanfriendly", format_size=lambda n: f"{n} B")
+        _stub_module("gcloud", get_instance=_cloud_only, ssh_connection=_cloud_only, get_instance_external_ip=_cloud_only,
+                     get_instance_internal_ip=_cloud_only, SSH_USER="nobody")
+        _stub_module("pickle_training", pack_arguments_to_pickle=_cloud_only, unpack_base64_pickle=_cloud_only)
+    import workers  # noqa
+    return workers
+
+
+def load_main():
+    """The reference's main.py (CircularArray, training loop) - needs the workers stubs and a `Net.NNet.NNetWrapper`."""
+    load_workers()
+    if "googleapiclient.discovery" not in sys.modules:
+        g = sys.modules.get("googleapiclient") or _stub_module("googleapiclient")
+        g.__path__ = []
+        g.discovery = _stub_module("googleapiclient.discovery")
+    import main  # noqa
+    return main
