@@ -178,18 +178,179 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synthetic_starts(engine_mod, n_games, seed, first_id, device):
-    """initial position + k in [0,8) random plies, k = slot % 8."""
+def synthetic_starts(engine_mod, n_games, seed, first_id, device, spread=8):
+    """Start positions: the initial position + k random plies (config-2 RNG), k = game index % spread.
+    spread = 8  : SURVEY 8d config 3's de-correlated OPENING starts;
+    spread = 57 : games of EVERY phase (0..56 plies played) - what a long-running self-play job holds at any moment."""
     b = np.zeros(n_games, dtype=np.uint64)
     w = np.zeros(n_games, dtype=np.uint64)
     p = np.zeros(n_games, dtype=np.int32)
-    for k in range(8):
-        sel = np.arange(n_games) % 8 == k
+    init = engine_mod.perft_playouts(1, 8, seed=seed, first_game_id=first_id, max_moves=0, device=device)
+    for k in range(spread):
+        sel = np.arange(n_games) % spread == k
         if not sel.any():
             continue
         out = engine_mod.perft_playouts(n_games, 8, seed=seed, first_game_id=first_id, max_moves=k, device=device)
-        b[sel] = out["black"][sel]; w[sel] = out["white"][sel]; p[sel] = out["player"][sel]
+        ok = sel & ~out["finished"]                      # a playout that ended early restarts from the initial position
+        b[sel], w[sel], p[sel] = init["black"][0], init["white"][0], 0
+        b[ok] = out["black"][ok]; w[ok] = out["white"][ok]; p[ok] = out["player"][ok]
     return b, w, p
+
+
+def l2_bandwidth(torch, device, mb=24, reps=60):
+    """Measured L2 bandwidth on this GPU: a 24 MB buffer (L2-resident: B200 has 126 MB) read by torch.sum, and copied
+    (read + write) by Tensor.copy_, timed with CUDA events.  The denominator of the table gather's roofline."""
+    x = torch.empty(mb << 18, dtype=torch.float32, device=device).normal_()
+    y = torch.empty_like(x)
+    out = {}
+    for name, fn, nbytes in (("read", lambda: x.sum(), x.numel() * 4), ("copy", lambda: y.copy_(x), x.numel() * 8)):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_gbs"] = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    out["what"] = f"{mb} MB L2-resident buffer, torch.sum (read) / Tensor.copy_ (read+write), {reps} launches each"
+    return out
+
+
+class Ctx:
+    pass
+
+
+def selfplay_leg(cx, *, games, sims, vl, cache_log2, window, steps, warmup, mode):
+    """One timed leg of the self-play hot path: `steps` x (STEPS_PER_MOVE engine steps) with `games` slots in flight.
+    window = "steady": slots start at every game phase and finished slots take queued games (steady-state mix);
+             "opening": every game starts within its first 8 plies (round 1's default window)."""
+    torch, dist, E, oznet, args = cx.torch, cx.dist, cx.E, cx.oznet, cx.args
+    n, C, G = 8, args.channels, games
+    spm = (sims + max(1, vl) - 1) // max(1, vl)
+    eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
+                   device=cx.local, eval_cache_log2=cache_log2 if mode == E.PRIOR_NET else 0, vl_width=vl)
+    try:
+        if mode == E.PRIOR_NET:
+            eng.load_weights_from_tensor(cx.wt, C)
+            eng.set_timing(True)
+        spread = 57 if window == "steady" else 8
+        # every slot always holds a game: a game lasts <= 60 moves, so 1 + (steps + warmup) // 30 queued generations
+        # are more than the timed region can consume
+        total = G * (2 + (steps + warmup) // 30)
+        first_id = cx.next_id + cx.rank * total
+        cx.next_id += cx.world * total
+        sb, sw, sp = synthetic_starts(E, total, args.seed, first_id, cx.local, spread)
+        ids = np.arange(first_id, first_id + total, dtype=np.uint64)
+        tree_only = mode == E.PRIOR_HASH
+        zero = {k: 0 for k in ("sims", "nodes", "moves", "cache_hits", "cache_aliases")}
+        stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{cx.local}")
+
+        def tree_batch():
+            # hash priors: a whole game runs inside ONE tree kernel launch, so a step is one complete batch of games
+            eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb[:G], sw[:G], sp[:G], ids[:G])
+            eng.selfplay_run(-1)
+            return eng.counters()
+
+        if not tree_only:
+            eng.selfplay_begin(total, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
+        for _ in range(warmup):
+            tree_batch() if tree_only else eng.selfplay_run(spm)
+        eng.layer_times()  # reset the per-layer accumulators
+        cx.barrier()
+        c0 = dict(zero) if tree_only else eng.counters()
+        l0 = eng.launches()
+        sampler = ClockSampler(cx.local)
+        if cx.rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        c1 = dict(zero)
+        for _ in range(steps):
+            if tree_only:
+                cc = tree_batch()
+                for k in c1:
+                    c1[k] += cc[k]
+            else:
+                eng.selfplay_run(spm)
+        ev1.record(stream)
+        cx.barrier()
+        clocks = sampler.stop() if cx.rank == 0 else None
+        ms = ev0.elapsed_time(ev1)
+        if not tree_only:
+            c1 = eng.counters()
+        l1 = eng.launches()
+        lt = eng.layer_times() if mode == E.PRIOR_NET else np.zeros(8, dtype=np.float32)
+        d = {k: c1[k] - c0[k] for k in zero}
+        d_evals = d["nodes"] - d["cache_hits"] - d["cache_aliases"]   # positions that actually went through the network
+        t = torch.tensor([ms, d["sims"], d_evals, d["moves"], l1 - l0, d["cache_hits"], d["cache_aliases"]],
+                         dtype=torch.float64, device=f"cuda:{cx.local}")
+        if cx.world > 1:
+            tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms = float(tmax[0]); tot = [float(x) for x in tsum[1:]]
+        else:
+            tot = [float(x) for x in t[1:]]
+        return dict(ms=ms, sims=tot[0], evals=tot[1], moves=tot[2], launches=tot[3], hits=tot[4], aliases=tot[5],
+                    evals_this_rank=float(d_evals), lt=lt, clocks=clocks, spm=spm, steps=steps, total_queued=int(total),
+                    engine=None)
+    finally:
+        eng.close()
+
+
+def tensor_roofline(cx, leg, C, conv2, conv3, peaks):
+    """`roofline` object of a PRIOR_NET leg: the dominant kernel (the conv3 implicit GEMM) against the measured cuBLAS
+    bf16 sustained peak, plus the whole-step tensor fraction and the per-layer times."""
+    lt, world = leg["lt"], cx.world
+    tree_steps = leg["steps"] * leg["spm"]
+    avg_leaves = leg["evals_this_rank"] / max(1, tree_steps)  # boards per forward
+    peak = peaks["bf16_sustained"]
+    cs = (C / 512.0) ** 2
+    table = conv2 == "table"
+    names = ["conv1_gather", "conv2_table_gather" if table else "conv2", "conv3", "conv4", "fc1", "fc2", "heads"]
+    layer_ms = {k: float(v) for k, v in zip(names, lt[:7])}
+    if table:
+        # conv1+conv2 are table reads, not tensor work: the dominant kernel is the conv3 implicit GEMM
+        k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm2_kernel (conv3 implicit GEMM, SM pair, split M tiles)"
+        traffic = ncu_traffic("oz_gemm2_kernel", "r1_ncu_final_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
+        tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8 - FLOP_CONV2_PER_BOARD_8
+        if conv3 == "wino":
+            # F(2,3) along y: 4 GEMMs with K = 3C instead of one with 9C -> 2/3 of the direct form's MACs are EXECUTED
+            k_flop = FLOP_CONV3_PER_BOARD_8 * 2 // 3
+            k_name = "oz_wino_kernel (conv3 as 1-D Winograd F(2,3), SM pair; executed FLOPs = 2/3 of the direct form)"
+            traffic = ncu_traffic("oz_wino_kernel", "r1_ncu_wino_raw.csv", 4096 * (96 + 36) * 512 * 2 + 12 * 512 * 512 * 2)
+            tensor_flop_per_eval -= FLOP_CONV3_PER_BOARD_8 // 3
+    else:
+        k_ms, k_flop, k_name = float(lt[1]), FLOP_CONV2_PER_BOARD_8, "oz_gemm2_kernel (conv2 implicit GEMM, SM pair)"
+        traffic = ncu_traffic("oz_gemm2_kernel")
+        tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8
+    achieved = k_flop * cs * avg_leaves / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    ms = leg["ms"]
+    roof = {"bound": "tensor", "kernel": k_name,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": traffic,
+            "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+            "note": "peak = cuBLAS bf16 measured back to back for 4 s (power-limited clock); frac > 1 means this "
+                    "kernel, timed inside a step that also holds lower-power kernels, runs at a higher clock "
+                    "than cuBLAS sustains - both sit at the 1 kW cap",
+            "avg_boards_per_launch": avg_leaves, "avg_launch_ms": k_ms,
+            "layer_ms": layer_ms, "forwards_timed": int(lt[7]),
+            "tensor_flop_per_eval": tensor_flop_per_eval * cs,
+            "whole_step_tensor_frac": (leg["evals"] / world) * tensor_flop_per_eval * cs / (ms * 1e-3) / 1e12 / peak,
+            "dense_equivalent_tflops": (leg["evals"] / world) * FLOP_PER_EVAL_8 * cs / (ms * 1e-3) / 1e12}
+    gather = None
+    if table and lt[1] > 0:
+        gb = GATHER_BYTES_PER_BOARD_8 * (C / 512.0) * avg_leaves / (float(lt[1]) * 1e-3) / 1e9
+        l2 = cx.l2
+        gather = {"bound": "l2", "kernel": "conv2_table_gather_kernel (conv1+conv2 as 484 table-row reads per board)",
+                  "achieved": gb, "peak": l2["read_gbs"], "unit": "GB/s", "frac": gb / l2["read_gbs"],
+                  "peak_source": "measured in this run: " + l2["what"], "l2_copy_gbs": l2["copy_gbs"],
+                  "avg_launch_ms": float(lt[1]),
+                  "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_final_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
+                  "note": "achieved = ALGORITHMIC row bytes (548 KB per board) / launch time; the rows are served by L1 (ncu: 57 % "
+                          "of the sectors) and L2 (DRAM reads are ~4 % of the algorithmic bytes), so the binding unit is the "
+                          "L2->SM path, not HBM; a frac near or above 1 means L1 hits carry part of the traffic"}
+    return roof, gather
 
 
 def run_ours(args):
@@ -211,7 +372,6 @@ def run_ours(args):
     n, C, sims, G = 8, args.channels, args.sims, args.games
     if args.e2e_games <= 0:
         args.e2e_games = 2 * G
-    STEPS_PER_MOVE = (sims + max(1, args.vl) - 1) // max(1, args.vl)
 
     def barrier():
         if world > 1:
@@ -219,109 +379,62 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     if args.workload == "perft":
-        return run_perft(args, E, peaks, rank, world, local, barrier)
+        line = perft_leg(args, E, peaks, rank, world, local, barrier, args.steps, args.warmup)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        if rank == 0:
+            if not args.no_cpu:
+                line["cpu_baseline"] = perft_cpu_sample()
+            print(json.dumps(line))
+        return
 
+    cx = Ctx()
+    cx.torch, cx.dist, cx.E, cx.oznet, cx.args = torch, dist, E, oznet, args
+    cx.world, cx.rank, cx.local, cx.barrier, cx.next_id = world, rank, local, barrier, 0
     mode = E.PRIOR_NET if args.workload == "selfplay" else E.PRIOR_HASH
-    eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
-                   device=local, eval_cache_log2=args.eval_cache_log2 if mode == E.PRIOR_NET else 0, vl_width=args.vl)
+    cx.wt = None
     if mode == E.PRIOR_NET:
         # C1: rank 0 owns the weights, everyone else receives them over NCCL and folds them on device
         nfl = oznet.blob_size(n, C)
         if rank == 0:
-            wt = torch.from_numpy(oznet.init_weights(n, C, seed=0)).cuda(local)
+            cx.wt = torch.from_numpy(oznet.init_weights(n, C, seed=0)).cuda(local)
         else:
-            wt = torch.empty(nfl, dtype=torch.float32, device=f"cuda:{local}")
+            cx.wt = torch.empty(nfl, dtype=torch.float32, device=f"cuda:{local}")
         if world > 1:
-            dist.broadcast(wt, src=0)
+            dist.broadcast(cx.wt, src=0)
         torch.cuda.synchronize()
-        eng.load_weights_from_tensor(wt, C)
-        eng.set_timing(True)
-    # The timed region always finds G games in flight: with the default K/W every game is still in its opening, and for a
-    # long run (K + W beyond ~40 moves, where episodes start to end) the device-side queue refills the slots, so `value`
-    # degrades into the steady-state mix of game phases instead of into idle slots.
-    total = G * (1 + (args.steps + args.warmup) // 40)
-    first_id = rank * total
-    sb, sw, sp = synthetic_starts(E, total, args.seed, first_id, local)
-    ids = np.arange(first_id, first_id + total, dtype=np.uint64)
-    eng.selfplay_begin(total, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
-
-    stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{local}")
+        cx.l2 = l2_bandwidth(torch, f"cuda:{local}")
     tree_only = mode == E.PRIOR_HASH
-    zero = {k: 0 for k in ("sims", "nodes", "moves", "cache_hits", "cache_aliases")}
-
-    def tree_batch():
-        # hash priors: a whole game runs inside ONE tree kernel launch, so a step is one complete batch of games
-        eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb[:G], sw[:G], sp[:G], ids[:G])
-        eng.selfplay_run(-1)
-        return eng.counters()
-
-    for _ in range(args.warmup):
-        tree_batch() if tree_only else eng.selfplay_run(STEPS_PER_MOVE)
-    eng.layer_times()  # reset the per-layer accumulators
-    barrier()
-    c0 = dict(zero) if tree_only else eng.counters()
-    l0 = eng.launches()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    c1 = dict(zero)
-    for _ in range(args.steps):
-        if tree_only:
-            cc = tree_batch()
-            for k in c1:
-                c1[k] += cc[k]
-        else:
-            eng.selfplay_run(STEPS_PER_MOVE)
-    ev1.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    if not tree_only:
-        c1 = eng.counters()
-    l1 = eng.launches()
-    lt = eng.layer_times() if mode == E.PRIOR_NET else np.zeros(8, dtype=np.float32)
-    d_sims = c1["sims"] - c0["sims"]; d_nodes = c1["nodes"] - c0["nodes"]; d_moves = c1["moves"] - c0["moves"]
-    d_hits = c1["cache_hits"] - c0["cache_hits"]; d_alias = c1["cache_aliases"] - c0["cache_aliases"]
-    d_evals = d_nodes - d_hits - d_alias  # positions that actually went through the network
-    tree_steps = args.steps * STEPS_PER_MOVE
-
-    t = torch.tensor([ms, float(d_sims), float(d_evals), float(d_moves), float(l1 - l0), float(d_hits), float(d_alias)],
-                     dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0]); tot_sims, tot_nodes, tot_moves, tot_launch, tot_hits, tot_alias = (float(x) for x in tsum[1:])
-    else:
-        tot_sims, tot_nodes, tot_moves, tot_launch, tot_hits, tot_alias = (float(d_sims), float(d_evals), float(d_moves),
-                                                                          float(l1 - l0), float(d_hits), float(d_alias))
-    sims_per_s = tot_sims / (ms / 1e3)
+    leg = selfplay_leg(cx, games=G, sims=sims, vl=args.vl, cache_log2=args.eval_cache_log2, window=args.window,
+                       steps=args.steps, warmup=args.warmup, mode=mode)
+    ms = leg["ms"]
+    sims_per_s = leg["sims"] / (ms / 1e3)
 
     # ---- e2e: complete games through the public API with HOST buffers (copies inside) ----------------------------
-    e2e = None
-    if not args.no_e2e:
-        # cold start: fresh games (other ids / start positions) and an EMPTY evaluation cache (reloading the weights
-        # clears it), so nothing evaluated during the timed region above can be reused here
-        if mode == E.PRIOR_NET:
-            eng.load_weights_from_tensor(wt, C)
+    e2e, rec = None, None
+    if not args.no_e2e and not tree_only:
+        # a fresh engine: fresh games (other ids / start positions) and an EMPTY evaluation cache, so nothing evaluated
+        # during the timed region above can be reused here
+        eng = E.Engine(n, max_games=G, nodes_per_game=sims * 61 + 64, prior_mode=mode, c_puct=1.0, seed=args.seed,
+                       device=local, eval_cache_log2=args.eval_cache_log2, vl_width=args.vl)
+        eng.load_weights_from_tensor(cx.wt, C)
         # e2e_games may exceed the G slots: the engine queues the rest and refills slots as episodes end
         NE = args.e2e_games
-        e_first = (1 << 24) + rank * NE
+        e_first = (1 << 40) + rank * NE
         sb, sw, sp = synthetic_starts(E, NE, args.seed + 1, e_first, local)
         ids = np.arange(e_first, e_first + NE, dtype=np.uint64)
         barrier()
         t0 = time.perf_counter()
-        eng.selfplay_begin(args.e2e_games, sims, 1.0, 0.9, args.e2e_moves, sb[:args.e2e_games], sw[:args.e2e_games],
-                           sp[:args.e2e_games], ids[:args.e2e_games])                      # H2D start positions
+        eng.selfplay_begin(NE, sims, 1.0, 0.9, args.e2e_moves, sb, sw, sp, ids)             # H2D start positions
         cb = eng.counters()
         eng.selfplay_run(-1)
         rec = eng.selfplay_records()                                                       # D2H example records
         ce = eng.counters()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        eng.close()
         e_sims = ce["sims"] - cb["sims"]
-        h2d = int(sb[:args.e2e_games].nbytes + sw[:args.e2e_games].nbytes + sp[:args.e2e_games].nbytes + ids[:args.e2e_games].nbytes)
+        h2d = int(sb.nbytes + sw.nbytes + sp.nbytes + ids.nbytes)
         d2h = int(sum(rec[k].nbytes for k in ("black", "white", "action", "player", "n_moves", "winner")))
         te = torch.tensor([dt, float(e_sims), float((rec["winner"] >= 0).sum()), float(rec["n_moves"].sum())],
                           dtype=torch.float64, device=f"cuda:{local}")
@@ -332,22 +445,62 @@ def run_ours(args):
         else:
             e_games, e_moves = float(te[2]), float(te[3])
         e2e = {"value": e_sims / dt, "unit": "sims/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "games_per_s": e_games / dt, "games": int(e_games), "mean_plies": e_moves / max(1.0, args.e2e_games * world),
-               "seconds": dt, "slots": int(min(G, args.e2e_games)),
-               "what": f"{args.e2e_games} games/GPU through {min(G, args.e2e_games)} slots (finished slots take the next queued game), "
+               "games_per_s": e_games / dt, "games": int(e_games), "mean_plies": e_moves / max(1.0, NE * world),
+               "seconds": dt, "slots": int(min(G, NE)),
+               "what": f"{NE} complete games/GPU through {min(G, NE)} slots (finished slots take the next queued game), "
                        "from host start positions to host example records"
-                                      + ("" if args.e2e_moves < 0 else f", first {args.e2e_moves} moves")}
+                       + ("" if args.e2e_moves < 0 else f", first {args.e2e_moves} moves")}
     gathered = None
     if world > 1:
         # C2: all-gather of the packed example records over NCCL (outside the timed regions)
         from othellozero_b200 import dist as ozd
-        if e2e is not None:
+        if rec is not None:
             gathered = int(ozd.gather_examples(ozd.pack_records(rec)).shape[0])
         dist.barrier()
+
+    # ---- extras (N = 1): the other configurations the driver should witness, each a short leg with its own roofline ----
+    extras = {}
+    if world == 1 and not args.no_extras and not tree_only and args.vl <= 1:
+        def short(name, **kw):
+            try:
+                lg = selfplay_leg(cx, **kw)
+                r = {"value": lg["sims"] / (lg["ms"] / 1e3), "unit": "sims/s", "steps": lg["steps"], "ms_per_step": lg["ms"] / lg["steps"],
+                     "evals_per_sim": lg["evals"] / max(1.0, lg["sims"]), "net_evals_per_s": lg["evals"] / (lg["ms"] / 1e3)}
+                if kw["mode"] == E.PRIOR_NET:
+                    roof, _ = tensor_roofline(cx, lg, C, args.conv2, args.conv3, peaks)
+                    r["roofline"] = {k: roof[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "avg_boards_per_launch",
+                                                          "avg_launch_ms", "whole_step_tensor_frac", "layer_ms")}
+                else:
+                    r["roofline"] = {"bound": "latency (declared against hbm)", "kernel": "tree_step_kernel",
+                                     "achieved": r["value"] * 1000 / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": r["value"] * 1000 / 1e9 / peaks["hbm_gbs"],
+                                     "note": "algorithmic ~1.0 KB/sim (SURVEY 8d); the kernel is instruction-issue/latency bound, not bandwidth bound"}
+                extras[name] = r
+            except Exception as ex:  # an extra must never cost the headline line
+                extras[name] = {"error": repr(ex)[:300]}
+        short("opening_window", games=G, sims=sims, vl=1, cache_log2=args.eval_cache_log2, window="opening", steps=5, warmup=3, mode=E.PRIOR_NET)
+        extras["opening_window"]["what"] = "round 1's default window: every game within its first ~16 plies, where the evaluation cache shares most"
+        short("cache_off", games=G, sims=sims, vl=1, cache_log2=0, window="steady", steps=5, warmup=3, mode=E.PRIOR_NET)
+        extras["cache_off"]["what"] = "same workload without the cross-game evaluation cache: one network evaluation per expanded node"
+        short("config3_vl8", games=512, sims=800, vl=8, cache_log2=args.eval_cache_log2, window="opening", steps=3, warmup=3, mode=E.PRIOR_NET)
+        extras["config3_vl8"]["what"] = ("BASELINE.json configs[3] on ONE GPU: 800 sims/move, 512 games, virtual-loss waves of 8 (visit counts "
+                                        "differ from the sequential reference by design)")
+        short("tree_only", games=G, sims=sims, vl=1, cache_log2=0, window="opening", steps=2, warmup=1, mode=E.PRIOR_HASH)
+        extras["tree_only"]["what"] = "rules + tree kernels alone (closed-form priors, no network): complete batches of 4096 games"
+        try:
+            pl = perft_leg(args, E, peaks, rank, world, local, barrier, 5, 3)
+            extras["perft"] = {k: pl[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e")}
+            extras["perft"]["what"] = "BASELINE.json configs[1]: 1M concurrent random playouts per launch"
+        except Exception as ex:
+            extras["perft"] = {"error": repr(ex)[:300]}
+    if world > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
 
+    window_txt = ("steady-state mix: slot s starts after (s % 57) random plies, so the timed region always holds games of every "
+                  "phase; finished slots take queued games" if args.window == "steady" else
+                  "opening window: every game starts within its first 8 plies")
     out = {
         "metric": "mcts_sims_per_sec", "value": sims_per_s, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -358,71 +511,33 @@ def run_ours(args):
                    if mode == E.PRIOR_NET else
                    "8x8 self-play tree+rules only, closed-form hash priors (no network)",
                    "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
-                   "eval_cache_log2": args.eval_cache_log2, "vl_width": args.vl,
-                   "step": (f"{STEPS_PER_MOVE} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
+                   "eval_cache_log2": args.eval_cache_log2, "vl_width": args.vl, "window": window_txt,
+                   "step": (f"{leg['spm']} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
                             if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 432 / 1e9),
-                   "starts": "initial position + (game_id % 8) random plies", "games_queued_per_gpu": int(total), "parallelism": f"games sharded x{world}"},
-        "moves_per_s": tot_moves / (ms / 1e3), "games_per_s_est": tot_moves / (ms / 1e3) / 60.0,
-        "net_evals_per_s": tot_nodes / (ms / 1e3), "evals_per_sim": tot_nodes / max(1.0, tot_sims),
-        "eval_cache": {"log2_entries": args.eval_cache_log2, "hits": int(tot_hits), "same_step_shares": int(tot_alias),
+                   "games_queued_per_gpu": leg["total_queued"], "parallelism": f"games sharded x{world}"},
+        "moves_per_s": leg["moves"] / (ms / 1e3), "games_per_s_est": leg["moves"] / (ms / 1e3) / 60.0,
+        "net_evals_per_s": leg["evals"] / (ms / 1e3), "evals_per_sim": leg["evals"] / max(1.0, leg["sims"]),
+        "eval_cache": {"log2_entries": args.eval_cache_log2, "hits": int(leg["hits"]), "same_step_shares": int(leg["aliases"]),
                        "note": "identical positions are evaluated once across games; outputs are unchanged"},
-        "gpu_launches": int(tot_launch), "clocks": clocks,
+        "gpu_launches": int(leg["launches"]), "clocks": leg["clocks"],
     }
     if gathered is not None:
         out["nccl"] = {"weights_broadcast_floats": int(oznet.blob_size(n, C)) if mode == E.PRIOR_NET else 0,
                        "examples_gathered": gathered}
     if mode == E.PRIOR_NET:
-        avg_leaves = (d_evals / max(1, tree_steps))  # boards per forward
-        peak = peaks["bf16_sustained"]
-        cs = (C / 512.0) ** 2
-        table = args.conv2 == "table"
-        names = ["conv1_gather", "conv2_table_gather" if table else "conv2", "conv3", "conv4", "fc1", "fc2", "heads"]
-        layer_ms = {k: float(v) for k, v in zip(names, lt[:7])}
-        if table:
-            # conv1+conv2 are table reads, not tensor work: the dominant kernel is the conv3 implicit GEMM
-            k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm2_kernel (conv3 implicit GEMM, SM pair, split M tiles)"
-            traffic = ncu_traffic("oz_gemm2_kernel", "r1_ncu_final_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
-            tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8 - FLOP_CONV2_PER_BOARD_8
-            if args.conv3 == "wino":
-                # F(2,3) along y: 4 GEMMs with K = 3C instead of one with 9C -> 2/3 of the direct form's MACs are EXECUTED
-                k_flop = FLOP_CONV3_PER_BOARD_8 * 2 // 3
-                k_name = "oz_wino_kernel (conv3 as 1-D Winograd F(2,3), SM pair; executed FLOPs = 2/3 of the direct form)"
-                traffic = ncu_traffic("oz_wino_kernel", "r1_ncu_wino_raw.csv", 4096 * (96 + 36) * 512 * 2 + 12 * 512 * 512 * 2)
-                tensor_flop_per_eval -= FLOP_CONV3_PER_BOARD_8 // 3
-        else:
-            k_ms, k_flop, k_name = float(lt[1]), FLOP_CONV2_PER_BOARD_8, "oz_gemm2_kernel (conv2 implicit GEMM, SM pair)"
-            traffic = ncu_traffic("oz_gemm2_kernel")
-            tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8
-        achieved = k_flop * cs * avg_leaves / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-        out["roofline"] = {"bound": "tensor", "kernel": k_name,
-                           "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                           "peak_source": f"{peaks['source']} cuBLAS bf16 sustained", "traffic": traffic,
-                           "frac_of_burst_peak": achieved / peaks["bf16_burst"],
-                           "note": "peak = cuBLAS bf16 measured back to back for 4 s (power-limited clock); frac > 1 means this "
-                                   "kernel, timed inside a step that also holds lower-power kernels, runs at a higher clock "
-                                   "than cuBLAS sustains - both sit at the 1 kW cap",
-                           "avg_boards_per_launch": avg_leaves, "avg_launch_ms": k_ms,
-                           "layer_ms": layer_ms, "forwards_timed": int(lt[7]),
-                           "tensor_flop_per_eval": tensor_flop_per_eval * cs,
-                           "whole_step_tensor_frac": (tot_nodes / world) * tensor_flop_per_eval * cs / (ms * 1e-3) / 1e12 / peak,
-                           "dense_equivalent_tflops": (tot_nodes / world) * FLOP_PER_EVAL_8 * cs / (ms * 1e-3) / 1e12}
-        if table and lt[1] > 0:
-            gb = GATHER_BYTES_PER_BOARD_8 * (C / 512.0) * avg_leaves / (float(lt[1]) * 1e-3) / 1e9
-            out["roofline_conv2_table"] = {
-                "bound": "hbm", "kernel": "conv2_table_gather_kernel (conv1+conv2 as 484 table-row reads per board)",
-                "achieved": gb, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
-                "avg_launch_ms": float(lt[1]),
-                "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_final_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
-                "note": "frac > 1 means the rows are served by L2/L1, not HBM (ncu: DRAM reads ~4 % of the algorithmic bytes); "
-                        "the kernel is latency-bound at ~44 % issue"}
+        out["roofline"], gather = tensor_roofline(cx, leg, C, args.conv2, args.conv3, peaks)
+        if gather:
+            out["roofline_conv2_table"] = gather
     else:
         out["roofline"] = {"bound": "hbm", "kernel": "tree_step_kernel", "achieved": sims_per_s / world * 1000 / 1e9,
                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": sims_per_s / world * 1000 / 1e9 / peaks["hbm_gbs"],
                            "traffic": None, "note": "algorithmic ~1.0 KB/sim (SURVEY §8d); latency- not bandwidth-bound"}
     if e2e:
         out["e2e"] = e2e
-    if not args.no_cpu and world >= 1:
+    if extras:
+        out["extras"] = extras
+    if not args.no_cpu and world == 1:
         out["cpu_baseline"] = cpu_sample(n, C, sims, moves=args.cpu_moves)
     print(json.dumps(out))
 
@@ -459,7 +574,9 @@ def perft_cpu_sample(games_per_proc=4000, procs=None):
                        f"restatement: {plies} plies in {wall:.1f}s")
 
 
-def run_perft(args, E, peaks, rank, world, local, barrier):
+def perft_leg(args, E, peaks, rank, world, local, barrier, steps, warmup):
+    """configs[1]: random-playout perft, 1M concurrent games per launch.  Returns the JSON line as a dict (rank 0) after the
+    max/sum over ranks; the caller owns the process group."""
     import ctypes as C
     import torch
     n_games = args.games if args.games > 4096 else (1 << 20)
@@ -471,7 +588,7 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
     def launch(seed):
         E.check(L.oz_perft_playouts_dev(8, seed, rank * n_games, n_games, -1, C.c_void_p(b.data_ptr()),
                                         C.c_void_p(w.data_ptr()), C.c_void_p(info.data_ptr()), None, None))
-    for i in range(args.warmup):
+    for i in range(warmup):
         launch(i)
     barrier()
     sampler = ClockSampler(local)
@@ -479,7 +596,7 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         launch(100 + i)
     ev1.record()
     barrier()
@@ -491,7 +608,7 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
         t_end, extended = time.time() + 3.0, False
         while len(sampler.lines) < 2 and time.time() < t_end:
             extended = True
-            for i in range(args.steps):
+            for i in range(steps):
                 launch(100 + i)
             torch.cuda.synchronize()
         clocks = sampler.stop()
@@ -499,7 +616,7 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
             clocks["note"] = "timed region shorter than the sampling period: sampled while the same launches were repeated untimed"
     # every launch plays different games (seed): replay the same seeds outside the timed region to count their plies
     plies = 0
-    for i in range(args.steps):
+    for i in range(steps):
         launch(100 + i)
         plies += int((info & 0xFF).sum().item())
     # e2e: the host-buffer entry point (results D2H inside the timed region), one launch
@@ -516,19 +633,16 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
         tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
         ms, dt, plies, e_plies = float(tm[0]), float(tm[2]), int(ts[1]), int(ts[3])
-        dist.barrier(); dist.destroy_process_group()
-    if rank != 0:
-        return
     value = plies / (ms / 1e3)
     f_sm = (clocks or {}).get("sm_mhz") or 1965.0
     peak = 148 * 4 * 32 * f_sm * 1e6 / 1e9          # thread-instructions / ns the SMs can issue at the sampled clock
     achieved = value / world * PERFT_THREAD_INSTR_PER_PLY / 1e9
-    line = {"metric": "perft_plies_per_sec", "value": value, "unit": "plies/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+    line = {"metric": "perft_plies_per_sec", "value": value, "unit": "plies/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "8x8 random-playout perft, %d concurrent games per GPU (BASELINE.json configs[1])" % n_games,
                        "l2": "state lives in registers for the whole game; 24 B written per game"},
-            "gpu_launches": args.steps, "clocks": clocks,
+            "gpu_launches": steps, "clocks": clocks,
             "roofline": {"bound": "int-issue", "kernel": "perft_playout_kernel", "achieved": achieved, "peak": peak,
                          "unit": "G thread-instr/s", "frac": achieved / peak, "traffic": None,
                          "note": "SURVEY 8d: the path is integer-issue bound, not HBM bound; achieved = plies/s x 624 counted "
@@ -537,9 +651,7 @@ def run_perft(args, E, peaks, rank, world, local, barrier):
             "e2e": {"value": e_plies / dt, "unit": "plies/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": int(n_games * 20), "calls": e_calls,
                     "what": "oz_perft_playouts_host with host buffers: one launch + final boards/info D2H per call (+ numpy unpacking)"}}
-    if not args.no_cpu:
-        line["cpu_baseline"] = perft_cpu_sample()
-    print(json.dumps(line))
+    return line
 
 
 def run_reference(args):
@@ -613,6 +725,11 @@ def main():
     ap.add_argument("--conv3", default="direct", choices=["direct", "wino"],
                     help="conv3 as the direct implicit GEMM (default) or as the opt-in Winograd F(2,3) kernel (DESIGN 3b)")
     ap.add_argument("--vl", type=int, default=1, help="virtual-loss wave width (configs[3]); 1 = sequential, bit-exact")
+    ap.add_argument("--window", default="steady", choices=["steady", "opening"],
+                    help="steady: slots start at every game phase (the steady-state mix of a long self-play job, independent of "
+                         "--steps/--warmup); opening: every game within its first plies (round 1's window)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short extra legs (opening window, cache off, configs[3] waves, tree only, perft) of the N=1 line")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

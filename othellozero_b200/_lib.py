@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "liboz_b200.so")
+# OZ_B200_LIB: another build of the same ABI (A/B runs of kernel variants); default = the in-tree library
+SO = os.environ.get("OZ_B200_LIB") or os.path.join(HERE, "liboz_b200.so")
 
 OZ_OK, OZ_ERR_INVALID, OZ_ERR_CUDA, OZ_ERR_NOMEM, OZ_ERR_STATE = 0, -1, -2, -3, -4
 PRIOR_HASH, PRIOR_HOST, PRIOR_NET = 0, 1, 2

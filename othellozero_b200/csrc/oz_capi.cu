@@ -149,6 +149,8 @@ extern "C" int oz_search_reset(oz_engine* e, int32_t n_games, const uint64_t* bl
     OZ_REQUIRE(e, "null engine");
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     e->tp.selfplay = 0;
+    e->tp.leaf_count = e->leaf_count_base;
+    e->tp.leaf_count_next = nullptr;
     e->search_started = false;
     int rc = oz_tree_reset(e, n_games, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
     if (rc) return rc;
@@ -179,7 +181,7 @@ __global__ void count_waiting_kernel(const OzTreeParams P, int* out) {
 }
 
 static int count_waiting(oz_engine* e, int* n) {
-    int* d = e->tp.leaf_count + 2;
+    int* d = e->leaf_count_base + 2;
     OZ_CUDA(cudaMemsetAsync(d, 0, sizeof(int), e->stream));
     count_waiting_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, d);
     OZ_CUDA(cudaGetLastError());
@@ -192,10 +194,9 @@ static int count_waiting(oz_engine* e, int* n) {
 
 // Evaluate the pending leaf batch with the device network (count stays on the device).
 static int eval_leaves_net(oz_engine* e) {
-    int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, e->leaf_logits,
-                            e->leaf_v);
-    if (rc) return rc;
-    return oz_tree_cache_publish(e);
+    // the heads kernel's epilogue publishes the new evaluation-cache entries (no separate cache_publish launch)
+    return oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, e->leaf_logits,
+                          e->leaf_v, e->tp.cache_tags != nullptr);
 }
 
 // Evaluate the parked leaves with whatever this engine's prior source is (device network / closed-form hash).
@@ -237,6 +238,8 @@ extern "C" int oz_search_begin(oz_engine* e, int32_t num_sims, int32_t* n_leaves
     if (e->host_leaves) { oz_set_error("pending leaves have not been answered"); return OZ_ERR_STATE; }
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     e->tp.selfplay = 0;
+    e->tp.leaf_count = e->leaf_count_base;
+    e->tp.leaf_count_next = nullptr;
     search_begin_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, num_sims);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
@@ -334,6 +337,8 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
     const int slots = n_games < e->cfg.max_games ? n_games : e->cfg.max_games;
     int rc = oz_tree_reserve_records(e, (size_t)n_games);
     if (rc) return rc;
+    e->tp.leaf_count = e->leaf_count_base;  // leaf counters ping-pong between [0] and [4] (oz_selfplay_run); reset clears [0]
+    e->tp.leaf_count_next = e->leaf_count_base + 4;
     rc = oz_tree_reset(e, slots, (const u64*)black, (const u64*)white, player, (const u64*)game_ids, true);
     if (rc) return rc;
     OzTreeParams& P = e->tp;
@@ -365,7 +370,7 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
     if (black) {
         // a start whose side to move has no legal move would never reach a move transition (MCTS.simulate of a root
         // without actions): refuse the job instead of silently dropping the game
-        int* bad = e->tp.leaf_count + 3;
+        int* bad = e->leaf_count_base + 3;
         e->h_pinned[6] = 0x7fffffff;
         OZ_CUDA(cudaMemcpyAsync(bad, &e->h_pinned[6], sizeof(int), cudaMemcpyHostToDevice, e->stream));
         validate_starts_kernel<<<(n_games + 255) / 256, 256, 0, e->stream>>>(n_games, P.q_black, P.q_white, P.q_player, P.full, bad);
@@ -379,6 +384,7 @@ extern "C" int oz_selfplay_begin(oz_engine* e, int32_t n_games, const uint64_t* 
     }
     P.total_games = n_games;
     e->rec_games = n_games;
+    OZ_CUDA(cudaMemsetAsync(P.leaf_count_next, 0, sizeof(int), e->stream));
     P.selfplay = 1;
     P.num_sims = num_sims;
     P.max_moves = max_moves;
@@ -415,10 +421,13 @@ extern "C" int oz_selfplay_run(oz_engine* e, int32_t steps, int32_t* n_active) {
         long long chunk = (steps < 0) ? 64 : (long long)steps - done;
         if (chunk > 64) chunk = 64;
         for (long long s = 0; s < chunk; ++s) {
-            OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, sizeof(int), e->stream));
+            // leaf counters ping-pong between [0] and [4]: each tree launch clears the one the next launch will fill
             int rc = oz_tree_step(e);
             if (rc) return rc;
             if (need_eval && (rc = eval_leaves(e))) return rc;
+            int* cur = P.leaf_count;
+            P.leaf_count = P.leaf_count_next;
+            P.leaf_count_next = cur;
         }
         done += chunk;
         OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[2], P.n_active, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -500,7 +509,7 @@ extern "C" int oz_net_forward_dev(oz_engine* e, const uint64_t* own, const uint6
     OZ_REQUIRE(n >= 1 && n <= e->max_leaves, "n %d out of range (capacity %d)", n, e->max_leaves);
     OZ_CUDA(cudaSetDevice(e->cfg.device));
     e->h_pinned[3] = n;
-    int* cnt = e->tp.leaf_count + 1;
+    int* cnt = e->leaf_count_base + 1;
     OZ_CUDA(cudaMemcpyAsync(cnt, &e->h_pinned[3], sizeof(int), cudaMemcpyHostToDevice, e->stream));
     int rc = oz_net_forward(e, (const u64*)own, (const u64*)opp, cnt, n, pi, logits ? logits : e->leaf_logits, v);
     if (rc) return rc;
@@ -517,7 +526,7 @@ extern "C" int oz_net_forward_host(oz_engine* e, const uint64_t* own, const uint
     OZ_CUDA(cudaMemcpyAsync(e->tp.leaf_own, own, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
     OZ_CUDA(cudaMemcpyAsync(e->tp.leaf_opp, opp, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
     e->h_pinned[3] = n;
-    int* cnt = e->tp.leaf_count + 1;
+    int* cnt = e->leaf_count_base + 1;
     OZ_CUDA(cudaMemcpyAsync(cnt, &e->h_pinned[3], sizeof(int), cudaMemcpyHostToDevice, e->stream));
     int rc = oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, cnt, n, e->leaf_pi, e->leaf_logits, e->leaf_v);
     if (rc) return rc;

@@ -70,6 +70,7 @@ struct OzTreeParams {
     int vl_width;                                                        // 1 = sequential (bit-exact) mode
     int sim_budget;  // self-play with an evaluator: simulations a game may complete per launch WITHOUT needing the evaluator
                      // (terminal visits, evaluation-cache hits) before it yields to the next step; 0 = unbounded
+    long long time_budget;  // ... and the age of the launch (SM clocks) after which such a game yields; 0 = unbounded
     u32* path_node; u32* path_edge;  // [G][vl_width][64]
     // pools
     unsigned char* arena; u64 arena_stride;  // bytes per game
@@ -77,6 +78,7 @@ struct OzTreeParams {
     u64* table; int table_log2;               // [G][1<<table_log2] : fingerprint<<32 | (node_off+1)
     // leaf batch
     u64* leaf_own; u64* leaf_opp; int* leaf_count; const float* leaf_pi; const float* leaf_v;
+    int* leaf_count_next;  // self-play: the counter of the next step, cleared by this step's tree kernel (or null)
     // cross-game evaluation cache (optional)
     u64* cache_tags; u64* cache_keys; int* cache_leaf; float* cache_pi; float* cache_v; int* leaf_cache_idx;
     int cache_log2_buckets;
@@ -123,6 +125,7 @@ struct oz_engine {
     float* leaf_v = nullptr;
     float* leaf_logits = nullptr;
     int* h_pinned = nullptr;   // small pinned scratch
+    int* leaf_count_base = nullptr;  // [8]: [0] leaf count, [1] net-forward count, [2] waiting games, [3] bad start, [4] second leaf count (self-play ping-pong)
     OzNet* net = nullptr;
     float layer_ms[8] = {0};
 };
@@ -136,7 +139,6 @@ int oz_tree_reserve_records(oz_engine* e, size_t games);
 int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev);
 int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev);
 int oz_tree_hash_eval(oz_engine* e);      // wave mode + closed-form priors: evaluate the parked leaves
-int oz_tree_cache_publish(oz_engine* e);  // after a leaf batch has been evaluated
 int oz_tree_cache_clear(oz_engine* e);    // weights changed
 
 // net (oz_net.cu)
@@ -144,8 +146,10 @@ int oz_net_create(oz_engine* e);
 void oz_net_destroy(oz_engine* e);
 int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels, bool on_device);
 // forward over `count_dev` (device int, <= max_games) canonical boards -> e->leaf_pi / leaf_logits / leaf_v
+// publish = true: the heads epilogue also copies every cache OWNER's priors into its evaluation-cache entry and marks
+// it ready (what cache_publish_kernel did in a launch of its own)
 int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const int* count_dev, int max_count,
-                   float* pi_dev, float* logits_dev, float* v_dev);
+                   float* pi_dev, float* logits_dev, float* v_dev, bool publish = false);
 int64_t oz_net_blob_floats_impl(int board_size, int channels);
 int oz_net_activation(oz_engine* e, int layer, void* host, int64_t bytes);
 void oz_net_set_timing_impl(oz_engine* e, bool on);

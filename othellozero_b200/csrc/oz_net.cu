@@ -64,6 +64,9 @@ struct GemmParams {
     bf16* out;
     float* pi; float* logits; float* v;  // heads
     int nsq;
+    // heads epilogue = also the evaluation cache's publish step (oz_tree.cu): row r of the batch belongs to cache entry
+    // cache_idx[r] (>= 0) whose owner parked it as "pending"; null = no cache
+    const int* cache_idx; float* cache_pi; float* cache_v; unsigned long long* cache_tags;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -414,7 +417,20 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
                         *reinterpret_cast<float4*>(prow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
                     }
-                    p.v[grow] = tanhf(nsq == 64 ? lg[64] : lg[36]);
+                    const float val = tanhf(nsq == 64 ? lg[64] : lg[36]);
+                    p.v[grow] = val;
+                    if (p.cache_idx) {
+                        const int cidx = p.cache_idx[grow];
+                        if (cidx >= 0) {  // this row's game owns a cache entry: fill it and mark it ready
+                            float* crow = p.cache_pi + (size_t)cidx * 64;
+#pragma unroll
+                            for (int j = 0; j < 64; j += 4)
+                                *reinterpret_cast<float4*>(crow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                            p.cache_v[cidx] = val;
+                            __threadfence();
+                            atomicOr(p.cache_tags + cidx, 1ull);  // pending (2) -> ready (3): fire and forget, no read round trip
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -1632,7 +1648,7 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
 }
 
 int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const int* count_dev, int max_count,
-                   float* pi_dev, float* logits_dev, float* v_dev) {
+                   float* pi_dev, float* logits_dev, float* v_dev, bool publish) {
     OzNet* net = e->net;
     if (!net || !net->loaded) { oz_set_error("network weights have not been loaded (oz_net_load_weights)"); return OZ_ERR_STATE; }
     cudaStream_t st = e->stream;
@@ -1682,6 +1698,10 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         static const char* lname[6] = {"conv2", "conv3", "conv4", "fc1", "fc2", "heads"};
         p.trace = trace_slot(net, lname[li]);
         p.pi = pi_dev; p.logits = logits_dev; p.v = v_dev;
+        if (publish && li == 5) {
+            p.cache_idx = e->tp.leaf_cache_idx; p.cache_pi = e->tp.cache_pi; p.cache_v = e->tp.cache_v;
+            p.cache_tags = e->tp.cache_tags;
+        }
         int tiles = ((max_count * p.tile_num + p.tile_den - 1) / p.tile_den) * p.n_tiles;
         int grid = tiles < net->sm_count ? tiles : net->sm_count;
         if (grid < 1) grid = 1;

@@ -31,6 +31,16 @@ using namespace ozbb;
 #define FULLW 0xffffffffu
 constexpr int TREE_WARPS = 4;  // warps (games) per CTA
 
+// ---- node references -----------------------------------------------------------------------------------------------
+// A node REFERENCE = (offset in 16-byte units << 6) | k, k = number of legal moves = number of child slots (<= 33).
+// Carrying k in the reference lets a descent issue the loads of a node's header AND of its P/Q/N/child rows in ONE
+// round (the row addresses depend on k): the pointer chase costs one memory latency per tree level instead of three
+// (header -> rows -> child[best]).  Child words >= 0, path entries, root_node[] and table_find's result are references.
+constexpr int REF_K_BITS = 6;
+__device__ __forceinline__ int make_ref(u32 off, int k) { return (int)((off << REF_K_BITS) | (u32)k); }
+__device__ __forceinline__ u32 ref_off(int ref) { return (u32)ref >> REF_K_BITS; }
+__device__ __forceinline__ int ref_k(int ref) { return ref & ((1 << REF_K_BITS) - 1); }
+
 __device__ __forceinline__ OzNodeHdr* node_at(unsigned char* arena, u32 off) {
     return (OzNodeHdr*)(arena + (size_t)off * 16);
 }
@@ -48,10 +58,34 @@ __device__ __forceinline__ u64 key_hash(u64 own, u64 opp) {
     return h;
 }
 
+// The bulky scalar helpers are REAL calls with by-value arguments and a by-value result (nothing is passed by pointer,
+// so no caller state is forced into local memory): every call site costs a few instructions instead of a few hundred,
+// which is what keeps the kernel's hot loops inside the instruction cache (round 1: ~10.3 K SASS instructions, fetch
+// stalls on top of the stall list).
+__device__ __noinline__ u64 flip_mask_call(u64 m, u64 own, u64 opp) { return flip_mask(m, own, opp); }
+__device__ __noinline__ u64 legal_moves_call(u64 own, u64 opp, u64 full) { return legal_moves(own, opp, full); }
+
+// play_move (oz_bitboard.cuh) over the out-of-line helpers.
+__device__ __forceinline__ unsigned play_move_dev(u64 m, u64& own, u64& opp, u64 full, u64& next_legal) {
+    const u64 f = flip_mask_call(m, own, opp);
+    own |= f | m;
+    opp &= ~f;
+    const u64 lo = legal_moves_call(opp, own, full);
+    if (lo) {
+        const u64 t = own; own = opp; opp = t;
+        next_legal = lo;
+        return MOVE_SWAPPED;
+    }
+    const u64 lm = legal_moves_call(own, opp, full);
+    next_legal = lm;
+    return lm ? MOVE_PASSED : MOVE_FINISHED;
+}
+
 // Warp-cooperative open-addressing lookup (32 slots per probe, one coalesced 256-byte load).
-// Returns node offset or -1; *ins = table slot where the key would be inserted.
-__device__ int table_find(const u64* __restrict__ table, int log2cap, unsigned char* arena, u64 own, u64 opp, int lane,
-                          u32* ins) {
+// Returns (insertion slot << 32) | (u32) reference; reference = -1 when the key is absent (the insertion slot is then
+// where it would go, 0xffffffff if the table is full).
+__device__ __noinline__ u64 table_find(const u64* __restrict__ table, int log2cap, unsigned char* arena, u64 own, u64 opp) {
+    const int lane = threadIdx.x & 31;
     u64 h = key_hash(own, opp);
     u32 mask = (1u << log2cap) - 1u;
     u32 fp = (u32)(h >> 32);
@@ -67,20 +101,18 @@ __device__ int table_find(const u64* __restrict__ table, int log2cap, unsigned c
             cand &= cand - 1u;
             u32 off = __shfl_sync(FULLW, (u32)ent, l) - 1u;
             OzNodeHdr* hd = node_at(arena, off);
-            if (hd->own == own && hd->opp == opp) return (int)off;
+            if (hd->own == own && hd->opp == opp) return (u64)(u32)make_ref(off, hd->k);
         }
-        if (empty) {
-            *ins = (start + w + (u32)(__ffs(empty) - 1)) & mask;
-            return -1;
-        }
+        if (empty) return ((u64)((start + w + (u32)(__ffs(empty) - 1)) & mask) << 32) | 0xffffffffull;
     }
-    *ins = 0xffffffffu;
-    return -1;
+    return 0xffffffffffffffffull;
 }
+__device__ __forceinline__ int find_ref(u64 r) { return (int)(u32)r; }
+__device__ __forceinline__ u32 find_ins(u64 r) { return (u32)(r >> 32); }
 
 // Per-warp registers that describe the simulation in flight.
 struct SimPath {
-    u32 n0, e0, n1, e1;  // lane l holds path entries l and l+32 : (node offset, child slot)
+    u32 n0, e0, n1, e1;  // lane l holds path entries l and l+32 : (node reference, child slot)
 };
 
 __device__ __forceinline__ void path_set(SimPath& p, int lane, int depth, u32 node, u32 edge) {
@@ -94,24 +126,25 @@ __device__ __forceinline__ void path_set(SimPath& p, int lane, int depth, u32 no
 // (is_int, iv, fv) = the value handed to the DEEPEST edge; it alternates sign going up (:71).
 constexpr int N_MASK = 0x00FFFFFF;  // low 24 bits of an N word = visits, high 8 bits = virtual (in-flight) visits
 
-__device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, int depth, bool is_int, int iv, float fv,
-                            bool vl) {
+__device__ __forceinline__ void backup_path(unsigned char* arena, const SimPath& p, int lane, int depth, bool is_int, int iv,
+                                            float fv, bool vl) {
     for (int t = lane; t < depth; t += 32) {
-        u32 noff = (t < 32) ? p.n0 : p.n1;
+        const int nref = (int)((t < 32) ? p.n0 : p.n1);
         u32 e = (t < 32) ? p.e0 : p.e1;
         bool neg = ((depth - 1 - t) & 1) != 0;
         int vi = neg ? -iv : iv;
         float vf = neg ? -fv : fv;
-        OzNodeHdr* h = node_at(arena, noff);
-        int k = h->k;
+        OzNodeHdr* h = node_at(arena, ref_off(nref));
+        const int k = ref_k(nref);  // no header round trip: Q/N addresses come from the reference
         double* Q = node_Q(h, k);
         int* N = node_N(h, k);
         const int nraw = N[e];
+        double q = Q[e];
+        const u64 qmask = h->qf32;
         const int nn = nraw & N_MASK;
         const int vn = (int)((unsigned)nraw >> 24);
-        double q = Q[e];
         u64 bit = 1ull << e;
-        bool f32 = (h->qf32 & bit) != 0ull;
+        bool f32 = (qmask & bit) != 0ull;
         if (nn == 0) {  // Q is python int 0
             if (is_int) {
                 q = __ddiv_rn((double)(0 + vi), 1.0);
@@ -136,7 +169,7 @@ __device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, in
         }
         Q[e] = q;
         N[e] = (nn + 1) | ((vl ? vn - 1 : vn) << 24);
-        if (f32) h->qf32 |= bit;
+        if (f32 && !(qmask & bit)) h->qf32 = qmask | bit;
         h->ns += 1;
         if (vl) h->vns -= 1;
     }
@@ -146,10 +179,10 @@ __device__ void backup_path(unsigned char* arena, const SimPath& p, int lane, in
 // A descent of a virtual-loss wave that ran into a leaf already in flight: take its virtual losses back.
 __device__ void revert_path(unsigned char* arena, const SimPath& p, int lane, int depth) {
     for (int t = lane; t < depth; t += 32) {
-        u32 noff = (t < 32) ? p.n0 : p.n1;
+        const int nref = (int)((t < 32) ? p.n0 : p.n1);
         u32 e = (t < 32) ? p.e0 : p.e1;
-        OzNodeHdr* h = node_at(arena, noff);
-        node_N(h, h->k)[e] -= (1 << 24);
+        OzNodeHdr* h = node_at(arena, ref_off(nref));
+        node_N(h, ref_k(nref))[e] -= (1 << 24);
         h->vns -= 1;
     }
     __syncwarp();
@@ -165,33 +198,30 @@ __device__ __forceinline__ float hash_v(u64 key) {
 
 struct Pending {
     u64 own, opp, legal;
-    int parent, pedge, depth;
+    int parent, pedge, depth;  // parent = reference of the parent node (-1: this leaf is the root)
 };
 
-// Expansion (MCTS/__init__.py:44-57) of `pd` with this lane's priors (pi_lo: square `lane`, pi_hi: square
-// lane+32), followed by the backup of -v.  Returns false when the node pool is exhausted.
-__device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, unsigned char* arena, u64* table,
-                                  const Pending& pd, float pi_lo, float pi_hi, float v, double* sa,
-                                  const SimPath& path, bool vl, bool* created) {
+// Expansion (MCTS/__init__.py:44-55) of `pd` with this lane's priors (pi_lo: square `lane`, pi_hi: square lane+32).
+// Returns 1 = node created, 0 = the position already had a node (only inside a virtual-loss wave: two edges of the wave led
+// to the same new position; this one just links to it), -1 = node pool / table exhausted.  The backup of -v is the caller's.
+__device__ __forceinline__ int expand_node(const OzTreeParams& P, int slot, int lane, unsigned char* arena, u64* table,
+                                           const Pending& pd, float pi_lo, float pi_hi, double* sa) {
     const int n = P.n, nsq = P.nsq;
-    int k = popc(pd.legal);
-    u32 units = node_units(k);
-    u32 off = P.bump[slot];
-    u32 ins;
-    int found = table_find(table, P.table_log2, arena, pd.own, pd.opp, lane, &ins);
-    *created = found < 0;
+    const int k = popc(pd.legal);
+    const u32 units = node_units(k);
+    const u32 off = P.bump[slot];
+    const u64 fr = table_find(table, P.table_log2, arena, pd.own, pd.opp);
+    const int found = find_ref(fr);
+    const u32 ins = find_ins(fr);
     if (found >= 0) {
-        // only in a virtual-loss wave: two edges of the wave led to the same new position; the first one created the
-        // node, this one just links to it and backs its (identical) value up
         if (lane == 0 && pd.parent >= 0) {
-            OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
-            node_child(ph, ph->k)[pd.pedge] = found;
+            OzNodeHdr* ph = node_at(arena, ref_off(pd.parent));
+            node_child(ph, ref_k(pd.parent))[pd.pedge] = found;
         }
         __syncwarp();
-        backup_path(arena, path, lane, pd.depth, false, 0, -v, vl);
-        return true;
+        return 0;
     }
-    if (((u64)off + units) * 16ull > P.arena_stride || ins == 0xffffffffu) return false;
+    if (((u64)off + units) * 16ull > P.arena_stride || ins == 0xffffffffu) return -1;
 
     // numpy order: a = pi(f32) * mask(f64) over the flat (N,N) array (othelo_mcts.py:69-73)
 #pragma unroll
@@ -240,16 +270,16 @@ __device__ bool expand_and_backup(const OzTreeParams& P, int slot, int lane, uns
         h->ns = 0; h->k = k; h->vns = 0; h->pad1 = 0;
         table[ins] = ((u64)(u32)(key_hash(pd.own, pd.opp) >> 32) << 32) | (u64)(off + 1u);
         P.bump[slot] = off + units;
+        const int ref = make_ref(off, k);
         if (pd.parent >= 0) {
-            OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
-            node_child(ph, ph->k)[pd.pedge] = (int)off;
+            OzNodeHdr* ph = node_at(arena, ref_off(pd.parent));
+            node_child(ph, ref_k(pd.parent))[pd.pedge] = ref;
         } else {
-            P.root_node[slot] = (int)off;
+            P.root_node[slot] = ref;
         }
     }
     __syncwarp();
-    backup_path(arena, path, lane, pd.depth, false, 0, -v, vl);  // MCTS:57 returns -v to the parent
-    return true;
+    return 1;
 }
 
 
@@ -270,7 +300,7 @@ __device__ __forceinline__ u64 cache_hash(u64 own, u64 opp) {
     return h;
 }
 
-__device__ int cache_probe(const OzTreeParams& P, u64 own, u64 opp, int lane, u64* fp_out, int* cidx, int* leaf) {
+__device__ __forceinline__ int cache_probe(const OzTreeParams& P, u64 own, u64 opp, int lane, u64* fp_out, int* cidx, int* leaf) {
     const u64 h = cache_hash(own, opp);
     const u64 fp = (h | (1ull << 63)) >> 2;  // 62 bits, never zero
     const u64 bucket = (h >> 3) & (((u64)1 << P.cache_log2_buckets) - 1ull);
@@ -310,27 +340,7 @@ __device__ int cache_probe(const OzTreeParams& P, u64 own, u64 opp, int lane, u6
     return CACHE_MISS;
 }
 
-// After the leaf batch has been evaluated: copy each owner's priors into its cache slot and mark it ready.
-__global__ void cache_publish_kernel(const OzTreeParams P) {
-    const int lane = threadIdx.x & 31;
-    const int li = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int L = *P.leaf_count;
-    if (li >= L) return;
-    const int idx = P.leaf_cache_idx[li];
-    if (idx < 0) return;
-    float* dst = P.cache_pi + (size_t)idx * 64;
-    const float* src = P.leaf_pi + (size_t)li * 64;
-    dst[lane] = src[lane];
-    dst[lane + 32] = src[lane + 32];
-    if (lane == 0) P.cache_v[idx] = P.leaf_v[li];
-    __syncwarp();
-    if (lane == 0) {
-        __threadfence();
-        u64 t = P.cache_tags[idx];
-        P.cache_tags[idx] = (t & ~3ull) | 3ull;
-    }
-}
-
+// Publishing (copying an owner's priors into its entry and marking it ready) is the heads kernel's epilogue: oz_net.cu.
 __device__ __forceinline__ void warp_argmax(double& u, int& j) {
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) {
@@ -340,14 +350,14 @@ __device__ __forceinline__ void warp_argmax(double& u, int& j) {
     }
 }
 
-// The engine step.  Every warp: (1) finishes the simulation that was waiting for its leaf, (2) keeps
-// simulating until it needs another network evaluation or runs out of work.
-// 8 CTAs (32 warps) per SM: at the compiler's natural 128 registers only 16 warps fit, so 4096 games needed 1.7 waves of a
-// latency-bound kernel; capped at 64 registers (~0.4 KB of spills per thread, L1-resident) all games are resident at once:
-// rules+tree workload 2.20e8 -> 2.49e8 sims/s, tree share of the self-play step 0.038 -> 0.030 ms (ncu: 1867 warp
-// instructions per simulation, issue 39 %, stalls dominated by instruction fetch and fixed-latency waits, not DRAM).
-// Turning the big helpers (play_move, table_find, expand_and_backup, backup_path) into real calls shrinks the kernel from
-// ~10 K to 6.8 K SASS instructions but is slower (2.30e8): pointer arguments force positions and paths into local memory.
+// The engine step.  Every warp: (1) finishes the simulations that were waiting for their leaves, (2) keeps simulating
+// until it needs another network evaluation or runs out of work.
+//
+// Structure (round 2): ONE loop whose body is either "expand the leaf at hand" or "run one descent", followed by ONE
+// shared backup site.  Every heavy piece of code - expansion, backup, transposition lookup, move application - exists
+// once in the kernel (round 1 had 3 inlined copies of the expansion, 5 of the backup, 3 of the lookup, 2 of play_move:
+// 10.3 K SASS instructions, the instruction fetch was the top stall reason).
+// 8 CTAs (32 warps) per SM: capped at 64 registers so that all 4096 games of configs[2] are resident at once.
 __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzTreeParams P) {
     __shared__ double s_a[TREE_WARPS][64];
     const int lane = threadIdx.x & 31;
@@ -356,8 +366,12 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
     if (slot >= P.G) return;
     double* sa = s_a[wib];
 
+    // self-play ping-pongs two leaf counters: this launch fills P.leaf_count and clears the one the NEXT launch fills
+    // (nobody reads it any more: the forward that consumed it ran before this launch) - no memset between steps
+    if (P.leaf_count_next && blockIdx.x == 0 && threadIdx.x == 0) *P.leaf_count_next = 0;
     int status = P.status[slot];
     if (status != OZ_GAME_ACTIVE && status != OZ_GAME_WAIT_LEAF) return;
+    const long long t_start = clock64();
 
     unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
     u64* table = P.table + ((size_t)slot << P.table_log2);
@@ -371,316 +385,327 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
 
     const int V = P.vl_width;
     const bool vl = V > 1;
-    if (status == OZ_GAME_WAIT_LEAF) {
-        // finish the simulations whose leaves have just been evaluated, in emission order (MCTS/__init__.py:44-57,67-71)
-        const int npend = P.pend_count[slot];
-        for (int i = 0; i < npend; ++i) {
-            const size_t pi_ = (size_t)slot * V + i;
-            pd.own = P.pend_own[pi_]; pd.opp = P.pend_opp[pi_]; pd.legal = P.pend_legal[pi_];
-            pd.parent = P.pend_parent[pi_]; pd.pedge = P.pend_edge[pi_]; pd.depth = P.pend_depth[pi_];
-            const int li = P.pend_leaf[pi_];
-            const u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
-            const u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
-            if (lane < pd.depth) { path.n0 = pn[lane]; path.e0 = pe[lane]; }
-            if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
-            // priors for this lane's two squares, row layout r*n+c with row stride 64
-            float pi_lo = 0.f, pi_hi = 0.f;
-            // li >= 0: row of the evaluated leaf batch; li <= -2: evaluation-cache entry -(li+2) (wave mode parks hits too)
-            const float* prow = (li >= 0) ? P.leaf_pi + (size_t)li * 64 : P.cache_pi + (size_t)(-(li + 2)) * 64;
-            {
-                int r = lane >> 3, c = lane & 7;
-                if (r < n && c < n) pi_lo = prow[r * n + c];
-                r += 4;
-                if (r < n && c < n) pi_hi = prow[r * n + c];
-            }
-            const float v = (li >= 0) ? P.leaf_v[li] : P.cache_v[-(li + 2)];
-            bool created;
-            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
-                if (lane == 0) P.status[slot] = OZ_GAME_POOL_FULL;
-                return;
-            }
-            c_nodes += created ? 1 : 0;
-            c_trans += created ? 0 : 1;
-            ++c_sims;
-            --sims_left;
-        }
-        status = OZ_GAME_ACTIVE;
-    }
+    // leaves parked by the previous launch, evaluated since: expanded first, in emission order (MCTS/__init__.py:44-57,67-71)
+    const int npend = (status == OZ_GAME_WAIT_LEAF) ? P.pend_count[slot] : 0;
+    int next_pend = 0;
+    status = OZ_GAME_ACTIVE;
     int inflight = 0;  // leaves parked by this launch (the current wave)
 
     u64 black = P.black[slot], white = P.white[slot];
     int player = P.player[slot];
     int ply = P.ply[slot];
 
+    // the leaf at hand: expanded by the next loop iteration.  src: 0 none, 1 priors in a global row, 2 closed-form hash priors
+    int exp_src = 0;
+    const float* exp_row = nullptr;
+    float exp_v = 0.f;
+    bool exp_counts_as_ran = false;
+
     int ran = 0;  // simulations completed by this launch without the evaluator
     while (true) {
-        if (P.selfplay && P.sim_budget > 0 && ran >= P.sim_budget) {  // yield: see oz_tree_alloc
-            status = inflight > 0 ? OZ_GAME_WAIT_LEAF : OZ_GAME_ACTIVE;
-            break;
-        }
-        if (sims_left - inflight <= 0) {
-            if (inflight > 0) { status = OZ_GAME_WAIT_LEAF; break; }
-            if (!P.selfplay) { status = OZ_GAME_IDLE; break; }
-            // ---- move transition: training.py:45-67 --------------------------------------------------
-            u64 own = player ? white : black, opp = player ? black : white;
-            int root = P.root_node[slot];
-            OzNodeHdr* h = node_at(arena, (u32)root);  // num_sims >= 2 guarantees the root exists
-            u64 legal = h->legal;
-            int k = h->k;
-            const int* Np = node_N(h, k);
-            // visit counts by child slot; first arg-max == np.argwhere(policy == policy.max())[0]
-            double best = -1.0; int bj = 1 << 20;
-            for (int j = lane; j < k; j += 32) {
-                double cnt = (double)(Np[j] & N_MASK);
-                if (cnt > best) { best = cnt; bj = j; }
+        // values handed to the shared backup site at the end of the iteration
+        bool do_backup = false, b_int = false;
+        int b_iv = 0, b_depth = 0;
+        float b_fv = 0.f;
+
+        if (next_pend < npend || exp_src) {
+            // ===== expansion site (the only one) =================================================================
+            if (!exp_src) {
+                const size_t pi_ = (size_t)slot * V + next_pend;
+                ++next_pend;
+                pd.own = P.pend_own[pi_]; pd.opp = P.pend_opp[pi_]; pd.legal = P.pend_legal[pi_];
+                pd.parent = P.pend_parent[pi_]; pd.pedge = P.pend_edge[pi_]; pd.depth = P.pend_depth[pi_];
+                const int li = P.pend_leaf[pi_];
+                const u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
+                const u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
+                if (lane < pd.depth) { path.n0 = pn[lane]; path.e0 = pe[lane]; }
+                if (lane + 32 < pd.depth) { path.n1 = pn[lane + 32]; path.e1 = pe[lane + 32]; }
+                // li >= 0: row of the evaluated leaf batch; li <= -2: evaluation-cache entry -(li+2) (wave mode parks hits too)
+                exp_row = (li >= 0) ? P.leaf_pi + (size_t)li * 64 : P.cache_pi + (size_t)(-(li + 2)) * 64;
+                exp_v = (li >= 0) ? P.leaf_v[li] : P.cache_v[-(li + 2)];
+                exp_src = 1;
+                exp_counts_as_ran = false;
             }
-            warp_argmax(best, bj);
-            const u64 base = episode_key(P.seed, P.game_id[slot]);
-            int aj = bj;
-            if (P.temperature == 0.0) {
-                // othelo_mcts.py:54-62: the policy is one-hot on random.choice(arg-max set); a unique maximum needs no
-                // draw, ties are broken by the game's counter RNG over the tied actions in row-major order
-                const unsigned t0 = __ballot_sync(FULLW, lane < k && (double)(Np[lane] & N_MASK) == best);
-                const unsigned t1 = __ballot_sync(FULLW, lane + 32 < k && (double)(Np[lane + 32] & N_MASK) == best);
-                const u64 ties = (u64)t0 | ((u64)t1 << 32);
-                const int nt = popc(ties);
-                if (nt > 1) aj = kth_set_bit(ties, (int)pick_index(episode_draw(base, ply, DRAW_TIE_BREAK), (u32)nt));
+            // priors for this lane's two squares (row layout r*n+c with row stride 64)
+            float pi_lo = 0.f, pi_hi = 0.f;
+            if (exp_src == 1) {
+                int r = lane >> 3, c = lane & 7;
+                if (r < n && c < n) pi_lo = exp_row[r * n + c];
+                r += 4;
+                if (r < n && c < n) pi_hi = exp_row[r * n + c];
+            } else {
+                const u64 key = sm64(pd.own ^ sm64(pd.opp));
+                pi_lo = hash_pi(key, lane); pi_hi = hash_pi(key, lane + 32);
+                exp_v = hash_v(key);
             }
-            const double coin = (double)(episode_draw(base, ply, DRAW_COIN) >> 11) * (1.0 / 9007199254740992.0);
-            if (!(coin <= P.e_greedy)) aj = (int)pick_index(episode_draw(base, ply, DRAW_RANDOM_ACTION), (u32)k);
-            int sq = kth_set_bit(legal, aj);
-            if (ply < 64) {
-                size_t ri = (size_t)gi * 64 + ply;
-                if (lane == 0) {
-                    P.rec_black[ri] = black; P.rec_white[ri] = white;
-                    P.rec_action[ri] = (unsigned char)sq; P.rec_player[ri] = (unsigned char)player;
+            exp_src = 0;
+            const int made = expand_node(P, slot, lane, arena, table, pd, pi_lo, pi_hi, sa);
+            if (made < 0) { status = OZ_GAME_POOL_FULL; break; }
+            c_nodes += made; c_trans += 1 - made;
+            if (exp_counts_as_ran) ++ran;
+            do_backup = true; b_int = false; b_fv = -exp_v; b_depth = pd.depth;  // MCTS:57 returns -v to the parent
+        } else {
+            // yield (see oz_tree_alloc): a game that keeps finding evaluator-free simulations (terminal visits, cache hits)
+            // stops once the launch has lasted `time_budget` clocks - by then the other games' warps have parked their
+            // leaves and the evaluator is waiting - or after `sim_budget` of them; it resumes at the same simulation
+            if (P.selfplay && ran > 0 &&
+                ((P.sim_budget > 0 && ran >= P.sim_budget) || (P.time_budget > 0 && clock64() - t_start > P.time_budget))) {
+                status = inflight > 0 ? OZ_GAME_WAIT_LEAF : OZ_GAME_ACTIVE;
+                break;
+            }
+            if (sims_left - inflight <= 0) {
+                if (inflight > 0) { status = OZ_GAME_WAIT_LEAF; break; }
+                if (!P.selfplay) { status = OZ_GAME_IDLE; break; }
+                // ---- move transition: training.py:45-67 --------------------------------------------------
+                u64 own = player ? white : black, opp = player ? black : white;
+                const int root = P.root_node[slot];
+                OzNodeHdr* h = node_at(arena, ref_off(root));  // num_sims >= 2 guarantees the root exists
+                const int k = ref_k(root);
+                const u64 legal = h->legal;
+                const int* Np = node_N(h, k);
+                // visit counts by child slot; first arg-max == np.argwhere(policy == policy.max())[0]
+                double best = -1.0; int bj = 1 << 20;
+                for (int j = lane; j < k; j += 32) {
+                    double cnt = (double)(Np[j] & N_MASK);
+                    if (cnt > best) { best = cnt; bj = j; }
                 }
-                if (P.log_visits) {
+                warp_argmax(best, bj);
+                const u64 base = episode_key(P.seed, P.game_id[slot]);
+                int aj = bj;
+                if (P.temperature == 0.0) {
+                    // othelo_mcts.py:54-62: the policy is one-hot on random.choice(arg-max set); a unique maximum needs no
+                    // draw, ties are broken by the game's counter RNG over the tied actions in row-major order
+                    const unsigned t0 = __ballot_sync(FULLW, lane < k && (double)(Np[lane] & N_MASK) == best);
+                    const unsigned t1 = __ballot_sync(FULLW, lane + 32 < k && (double)(Np[lane + 32] & N_MASK) == best);
+                    const u64 ties = (u64)t0 | ((u64)t1 << 32);
+                    const int nt = popc(ties);
+                    if (nt > 1) aj = kth_set_bit(ties, (int)pick_index(episode_draw(base, ply, DRAW_TIE_BREAK), (u32)nt));
+                }
+                const double coin = (double)(episode_draw(base, ply, DRAW_COIN) >> 11) * (1.0 / 9007199254740992.0);
+                if (!(coin <= P.e_greedy)) aj = (int)pick_index(episode_draw(base, ply, DRAW_RANDOM_ACTION), (u32)k);
+                const int sq = kth_set_bit(legal, aj);
+                if (ply < 64) {
+                    size_t ri = (size_t)gi * 64 + ply;
+                    if (lane == 0) {
+                        P.rec_black[ri] = black; P.rec_white[ri] = white;
+                        P.rec_action[ri] = (unsigned char)sq; P.rec_player[ri] = (unsigned char)player;
+                    }
+                    if (P.log_visits) {
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        int s = lane + 32 * half;
-                        int cnt = ((legal >> s) & 1ull) ? (Np[popc(legal & ((1ull << s) - 1ull))] & N_MASK) : 0;
-                        P.rec_visits[ri * 64 + s] = cnt;
+                        for (int half = 0; half < 2; ++half) {
+                            int s = lane + 32 * half;
+                            int cnt = ((legal >> s) & 1ull) ? (Np[popc(legal & ((1ull << s) - 1ull))] & N_MASK) : 0;
+                            P.rec_visits[ri * 64 + s] = cnt;
+                        }
                     }
                 }
-            }
-            u64 nl;
-            unsigned fl = play_move(1ull << sq, &own, &opp, P.full, &nl);
-            if (fl & MOVE_SWAPPED) player ^= 1;
-            black = player ? opp : own;
-            white = player ? own : opp;
-            ++ply; ++c_moves;
-            if (lane == 0) P.rec_nmoves[gi] = ply;
-            const bool over = (fl & MOVE_FINISHED) != 0;
-            if (over || (P.max_moves >= 0 && ply >= P.max_moves)) {
-                if (lane == 0) {
-                    P.winner[gi] = over ? ((popc(black) >= popc(white)) ? 0 : 1) : -1;
-                    if (ply < 64) {  // entry n_moves of a game's record row = the position the episode ended in
-                        P.rec_black[(size_t)gi * 64 + ply] = black; P.rec_white[(size_t)gi * 64 + ply] = white;
+                u64 nl;
+                const unsigned fl = play_move_dev(1ull << sq, own, opp, P.full, nl);
+                if (fl & MOVE_SWAPPED) player ^= 1;
+                black = player ? opp : own;
+                white = player ? own : opp;
+                ++ply; ++c_moves;
+                if (lane == 0) P.rec_nmoves[gi] = ply;
+                const bool over = (fl & MOVE_FINISHED) != 0;
+                if (over || (P.max_moves >= 0 && ply >= P.max_moves)) {
+                    if (lane == 0) {
+                        P.winner[gi] = over ? ((popc(black) >= popc(white)) ? 0 : 1) : -1;
+                        if (ply < 64) {  // entry n_moves of a game's record row = the position the episode ended in
+                            P.rec_black[(size_t)gi * 64 + ply] = black; P.rec_white[(size_t)gi * 64 + ply] = white;
+                        }
                     }
+                    // the episode is over: take the next queued game into this slot, or retire the slot
+                    int ng = P.total_games;
+                    if (lane == 0) ng = atomicAdd(P.next_game, 1);
+                    ng = __shfl_sync(FULLW, ng, 0);
+                    if (ng >= P.total_games) {
+                        status = OZ_GAME_FINISHED;
+                        if (lane == 0) atomicSub(P.n_active, 1);
+                        break;
+                    }
+                    gi = ng;
+                    if (P.q_black) { black = P.q_black[ng]; white = P.q_white[ng]; }
+                    else initial_position(n, &black, &white);
+                    player = P.q_player ? P.q_player[ng] : 0;
+                    ply = 0;
+                    uint4* t4 = reinterpret_cast<uint4*>(table);  // a fresh tree: empty table, empty pool (training.py:30-32)
+                    for (int i = lane; i < (1 << (P.table_log2 - 1)); i += 32) t4[i] = make_uint4(0, 0, 0, 0);
+                    if (lane == 0) {
+                        P.slot_game[slot] = ng;
+                        P.game_id[slot] = P.q_ids ? P.q_ids[ng] : (u64)ng;
+                        P.bump[slot] = 1;
+                        P.root_node[slot] = -1;
+                    }
+                    __syncwarp();
+                    sims_left = P.num_sims;
+                    continue;
                 }
-                // the episode is over: take the next queued game into this slot, or retire the slot
-                int ng = P.total_games;
-                if (lane == 0) ng = atomicAdd(P.next_game, 1);
-                ng = __shfl_sync(FULLW, ng, 0);
-                if (ng >= P.total_games) {
-                    status = OZ_GAME_FINISHED;
-                    if (lane == 0) atomicSub(P.n_active, 1);
-                    break;
-                }
-                gi = ng;
-                if (P.q_black) { black = P.q_black[ng]; white = P.q_white[ng]; }
-                else initial_position(n, &black, &white);
-                player = P.q_player ? P.q_player[ng] : 0;
-                ply = 0;
-                uint4* t4 = reinterpret_cast<uint4*>(table);  // a fresh tree: empty table, empty pool (training.py:30-32)
-                for (int i = lane; i < (1 << (P.table_log2 - 1)); i += 32) t4[i] = make_uint4(0, 0, 0, 0);
-                if (lane == 0) {
-                    P.slot_game[slot] = ng;
-                    P.game_id[slot] = P.q_ids ? P.q_ids[ng] : (u64)ng;
-                    P.bump[slot] = 1;
-                    P.root_node[slot] = -1;
-                }
+                const int nr = find_ref(table_find(table, P.table_log2, arena, own, opp));
+                if (lane == 0) P.root_node[slot] = nr;
                 __syncwarp();
                 sims_left = P.num_sims;
                 continue;
             }
-            u32 ins;
-            int nr = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
-            if (lane == 0) P.root_node[slot] = nr;
-            __syncwarp();
-            sims_left = P.num_sims;
-            continue;
-        }
 
-        if (inflight >= V) { status = OZ_GAME_WAIT_LEAF; break; }  // wave is full: wait for the evaluator
+            if (inflight >= V) { status = OZ_GAME_WAIT_LEAF; break; }  // wave is full: wait for the evaluator
 
-        // ---- one simulation: MCTS.simulate from the canonical root (othelo_mcts.py:22-26) -----------
-        int node = P.root_node[slot];
-        int depth = 0;
-        int outcome = 0;  // 1 = terminal, 2 = leaf
-        int term_val = 0;
-        if (node < 0) {
-            pd.own = player ? white : black;
-            pd.opp = player ? black : white;
-            pd.legal = legal_moves(pd.own, pd.opp, P.full);
-            pd.parent = -1; pd.pedge = 0; pd.depth = 0;
-            outcome = 2;
-            if (!pd.legal) {  // caller handed us a root whose side to move cannot move: nothing to simulate
-                status = P.selfplay ? OZ_GAME_FINISHED : OZ_GAME_IDLE;
-                if (P.selfplay && lane == 0) atomicSub(P.n_active, 1);
-                sims_left = 0;
-                break;
-            }
-        }
-        while (!outcome) {
-            OzNodeHdr* h = node_at(arena, (u32)node);
-            const int k = h->k;
-            const int ns = h->ns;
-            const double* Pp = node_P(h);
-            const double* Qp = node_Q(h, k);
-            int* Np = node_N(h, k);
-            int* Cp = node_child(h, k);
-            const double sq_ns = __dsqrt_rn((double)(ns + h->vns));
-            double bu = -1.0e300; int bj = 1 << 20;
-            for (int j = lane; j < k; j += 32) {
-                const int nraw = Np[j];
-                const int nj = nraw & N_MASK, vn = (int)((unsigned)nraw >> 24);
-                double q = Qp[j];
-                if (vn) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nj, q), -(double)vn), (double)(nj + vn));  // in-flight = losses
-                double bound = __ddiv_rn(sq_ns, (double)(1 + nj + vn));
-                double u = __dadd_rn(q, __dmul_rn(__dmul_rn(P.c, Pp[j]), bound));
-                if (u > bu) { bu = u; bj = j; }
-            }
-            warp_argmax(bu, bj);
-            path_set(path, lane, depth, (u32)node, (u32)bj);
-            ++depth;
-            if (vl) {  // leave a virtual loss on the chosen edge for the rest of the wave
-                if (lane == 0) { Np[bj] += (1 << 24); h->vns += 1; }
-                __syncwarp();
-            }
-            int ch = Cp[bj];
-            if (ch >= 0) { node = ch; continue; }
-            if (ch == OZ_CH_PENDING) { outcome = 3; break; }  // that leaf is already in flight in this wave
-            if (ch == OZ_CH_TERM_NEG || ch == OZ_CH_TERM_POS) {
-                term_val = (ch == OZ_CH_TERM_POS) ? 1 : -1;
-                outcome = 1;
-                break;
-            }
-            // frontier: get_next_state (othelo_mcts.py:43-49)
-            u64 own = h->own, opp = h->opp;
-            int sq = kth_set_bit(h->legal, bj);
-            u64 nl;
-            unsigned fl = play_move(1ull << sq, &own, &opp, P.full, &nl);
-            if (fl & MOVE_FINISHED) {
-                // is_terminal_state -> return -reward; reward = +1 iff ch0 count >= ch1 count (draw -> BLACK)
-                int reward = (popc(own) >= popc(opp)) ? 1 : -1;
-                term_val = -reward;
-                if (lane == 0) Cp[bj] = (term_val > 0) ? OZ_CH_TERM_POS : OZ_CH_TERM_NEG;
-                outcome = 1;
-                break;
-            }
-            u32 ins;
-            int found = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
-            if (found >= 0) {  // transposition: the state already has a node
-                if (lane == 0) Cp[bj] = found;
-                ++c_trans;
-                node = found;
-                continue;
-            }
-            pd.own = own; pd.opp = opp; pd.legal = nl;
-            pd.parent = node; pd.pedge = bj; pd.depth = depth;
-            outcome = 2;
-        }
-        if (depth > c_depth) c_depth = depth;
-        __syncwarp();
-
-        if (outcome == 3) {
-            revert_path(arena, path, lane, depth);
-            status = OZ_GAME_WAIT_LEAF;  // inflight > 0 here: pending edges only exist inside a wave
-            break;
-        }
-        if (outcome == 1) {
-            backup_path(arena, path, lane, depth, true, term_val, (float)term_val, vl);
-            ++c_term; ++c_sims; ++ran;
-            --sims_left;
-            continue;
-        }
-        // leaf
-        if (P.prior_mode == OZ_PRIOR_HASH && !vl) {
-            u64 key = sm64(pd.own ^ sm64(pd.opp));
-            float pi_lo = hash_pi(key, lane), pi_hi = hash_pi(key, lane + 32);
-            float v = hash_v(key);
-            bool created;
-            if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
-                status = OZ_GAME_POOL_FULL;
-                break;
-            }
-            ++c_nodes; ++c_sims;
-            --sims_left;
-            continue;
-        }
-        // hand the leaf to the evaluator and park this game (or reuse an evaluation of the same position)
-        int li = -1, cidx = -1, cres = CACHE_MISS;
-        u64 cfp = 0;
-        if (P.cache_tags) {
-            cres = cache_probe(P, pd.own, pd.opp, lane, &cfp, &cidx, &li);
-            if (cres == CACHE_HIT && vl) {
-                // wave mode: keep the wave's composition independent of the cache - park the hit like any other leaf
-                ++c_hits;
-                li = -(cidx + 2);
-            } else if (cres == CACHE_HIT) {
-                const int r = lane >> 3, c = lane & 7;
-                float pi_lo = 0.f, pi_hi = 0.f;
-                const float* row = P.cache_pi + (size_t)cidx * 64;
-                if (r < n && c < n) pi_lo = row[r * n + c];
-                if (r + 4 < n && c < n) pi_hi = row[(r + 4) * n + c];
-                const float v = P.cache_v[cidx];
-                bool created;
-                if (!expand_and_backup(P, slot, lane, arena, table, pd, pi_lo, pi_hi, v, sa, path, vl, &created)) {
-                    status = OZ_GAME_POOL_FULL;
+            // ---- one simulation: MCTS.simulate from the canonical root (othelo_mcts.py:22-26) -----------
+            int node = P.root_node[slot];
+            int depth = 0;
+            int outcome = 0;  // 1 = terminal, 2 = leaf, 3 = ran into a leaf of this wave
+            int term_val = 0;
+            if (node < 0) {
+                pd.own = player ? white : black;
+                pd.opp = player ? black : white;
+                pd.legal = legal_moves_call(pd.own, pd.opp, P.full);
+                pd.parent = -1; pd.pedge = 0; pd.depth = 0;
+                outcome = 2;
+                if (!pd.legal) {  // a root whose side to move cannot move (search API only; self-play starts are validated)
+                    status = P.selfplay ? OZ_GAME_FINISHED : OZ_GAME_IDLE;
+                    if (P.selfplay && lane == 0) atomicSub(P.n_active, 1);
+                    sims_left = 0;
                     break;
                 }
-                ++c_nodes; ++c_sims; ++c_hits; ++ran;
-                --sims_left;
+            }
+            while (!outcome) {
+                OzNodeHdr* h = node_at(arena, ref_off(node));
+                const int k = ref_k(node);
+                const double* Pp = node_P(h);
+                const double* Qp = node_Q(h, k);
+                int* Np = node_N(h, k);
+                int* Cp = node_child(h, k);
+                // ONE round of loads per level: header counters + this lane's P/Q/N/child (addresses need only the reference)
+                const int2 cnts = *reinterpret_cast<const int2*>(&h->ns);  // {ns, k}
+                const int vns = h->vns;
+                int c0 = OZ_CH_UNKNOWN, c1 = OZ_CH_UNKNOWN;
+                double bu = -1.0e300; int bj = 1 << 20;
+                const double sq_ns = __dsqrt_rn((double)(cnts.x + vns));
+                for (int j = lane; j < k; j += 32) {
+                    const int nraw = Np[j];
+                    const int cj = Cp[j];
+                    double q = Qp[j];
+                    const double pj = Pp[j];
+                    if (j < 32) c0 = cj; else c1 = cj;
+                    const int nj = nraw & N_MASK, vn = (int)((unsigned)nraw >> 24);
+                    if (vn) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nj, q), -(double)vn), (double)(nj + vn));  // in-flight = losses
+                    double bound = __ddiv_rn(sq_ns, (double)(1 + nj + vn));
+                    double u = __dadd_rn(q, __dmul_rn(__dmul_rn(P.c, pj), bound));
+                    if (u > bu) { bu = u; bj = j; }
+                }
+                warp_argmax(bu, bj);
+                path_set(path, lane, depth, (u32)node, (u32)bj);
+                ++depth;
+                if (vl) {  // leave a virtual loss on the chosen edge for the rest of the wave
+                    if (lane == 0) { Np[bj] += (1 << 24); h->vns = vns + 1; }
+                    __syncwarp();
+                }
+                const int ch = __shfl_sync(FULLW, (bj < 32) ? c0 : c1, bj & 31);  // child[best] came with the same round
+                if (ch >= 0) { node = ch; continue; }
+                if (ch == OZ_CH_PENDING) { outcome = 3; break; }  // that leaf is already in flight in this wave
+                if (ch == OZ_CH_TERM_NEG || ch == OZ_CH_TERM_POS) {
+                    term_val = (ch == OZ_CH_TERM_POS) ? 1 : -1;
+                    outcome = 1;
+                    break;
+                }
+                // frontier: get_next_state (othelo_mcts.py:43-49)
+                u64 own = h->own, opp = h->opp;
+                const int sq = kth_set_bit(h->legal, bj);
+                u64 nl;
+                const unsigned fl = play_move_dev(1ull << sq, own, opp, P.full, nl);
+                if (fl & MOVE_FINISHED) {
+                    // is_terminal_state -> return -reward; reward = +1 iff ch0 count >= ch1 count (draw -> BLACK)
+                    int reward = (popc(own) >= popc(opp)) ? 1 : -1;
+                    term_val = -reward;
+                    if (lane == 0) Cp[bj] = (term_val > 0) ? OZ_CH_TERM_POS : OZ_CH_TERM_NEG;
+                    outcome = 1;
+                    break;
+                }
+                const int found = find_ref(table_find(table, P.table_log2, arena, own, opp));
+                if (found >= 0) {  // transposition: the state already has a node
+                    if (lane == 0) Cp[bj] = found;
+                    ++c_trans;
+                    node = found;
+                    continue;
+                }
+                pd.own = own; pd.opp = opp; pd.legal = nl;
+                pd.parent = node; pd.pedge = bj; pd.depth = depth;
+                outcome = 2;
+            }
+            if (depth > c_depth) c_depth = depth;
+            __syncwarp();
+
+            if (outcome == 3) {
+                revert_path(arena, path, lane, depth);
+                status = OZ_GAME_WAIT_LEAF;  // inflight > 0 here: pending edges only exist inside a wave
+                break;
+            }
+            if (outcome == 1) {
+                ++c_term; ++ran;
+                do_backup = true; b_int = true; b_iv = term_val; b_fv = (float)term_val; b_depth = depth;
+            } else if (P.prior_mode == OZ_PRIOR_HASH && !vl) {
+                exp_src = 2; exp_counts_as_ran = false;  // closed-form priors: expanded by the next iteration
+                continue;
+            } else {
+                // hand the leaf to the evaluator and park this game (or reuse an evaluation of the same position)
+                int li = -1, cidx = -1, cres = CACHE_MISS;
+                u64 cfp = 0;
+                if (P.cache_tags) {
+                    cres = cache_probe(P, pd.own, pd.opp, lane, &cfp, &cidx, &li);
+                    if (cres == CACHE_HIT) {
+                        ++c_hits;
+                        if (vl) {
+                            li = -(cidx + 2);  // wave mode: keep the wave's composition independent of the cache - park the hit
+                        } else {
+                            exp_src = 1; exp_row = P.cache_pi + (size_t)cidx * 64; exp_v = P.cache_v[cidx];
+                            exp_counts_as_ran = true;
+                            continue;  // expanded by the next iteration, no network round trip
+                        }
+                    }
+                }
+                if (cres == CACHE_ALIAS) {
+                    ++c_alias;
+                } else if (li > -2) {
+                    if (lane == 0) li = atomicAdd(P.leaf_count, 1);
+                    li = __shfl_sync(FULLW, li, 0);
+                    if (lane == 0) {
+                        P.leaf_own[li] = pd.own; P.leaf_opp[li] = pd.opp;
+                        if (P.cache_tags) P.leaf_cache_idx[li] = (cres == CACHE_OWNER) ? cidx : -1;
+                        if (cres == CACHE_OWNER) {
+                            P.cache_keys[2 * (size_t)cidx] = pd.own; P.cache_keys[2 * (size_t)cidx + 1] = pd.opp;
+                            P.cache_leaf[cidx] = li;
+                            __threadfence();
+                            *((volatile u64*)P.cache_tags + cidx) = (cfp << 2) | 2ull;  // pending: same-step readers alias row li
+                        }
+                    }
+                }
+                {
+                    const size_t pi_ = (size_t)slot * V + inflight;
+                    if (lane == 0) {
+                        P.pend_own[pi_] = pd.own; P.pend_opp[pi_] = pd.opp; P.pend_legal[pi_] = pd.legal;
+                        P.pend_parent[pi_] = pd.parent; P.pend_edge[pi_] = pd.pedge; P.pend_depth[pi_] = pd.depth;
+                        P.pend_leaf[pi_] = li;
+                        if (vl && pd.parent >= 0) {  // later descents of this wave must not emit the same leaf again
+                            OzNodeHdr* ph = node_at(arena, ref_off(pd.parent));
+                            node_child(ph, ref_k(pd.parent))[pd.pedge] = OZ_CH_PENDING;
+                        }
+                    }
+                    u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
+                    u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
+                    if (lane < pd.depth) { pn[lane] = path.n0; pe[lane] = path.e0; }
+                    if (lane + 32 < pd.depth) { pn[lane + 32] = path.n1; pe[lane + 32] = path.e1; }
+                    __syncwarp();
+                }
+                ++inflight;
+                if (pd.parent < 0) { status = OZ_GAME_WAIT_LEAF; break; }  // the root itself: nothing else can run before it exists
                 continue;
             }
         }
-        if (cres == CACHE_ALIAS) {
-            ++c_alias;
-        } else if (li > -2) {
-            if (lane == 0) li = atomicAdd(P.leaf_count, 1);
-            li = __shfl_sync(FULLW, li, 0);
-            if (lane == 0) {
-                P.leaf_own[li] = pd.own; P.leaf_opp[li] = pd.opp;
-                if (P.cache_tags) P.leaf_cache_idx[li] = (cres == CACHE_OWNER) ? cidx : -1;
-                if (cres == CACHE_OWNER) {
-                    P.cache_keys[2 * (size_t)cidx] = pd.own; P.cache_keys[2 * (size_t)cidx + 1] = pd.opp;
-                    P.cache_leaf[cidx] = li;
-                    __threadfence();
-                    *((volatile u64*)P.cache_tags + cidx) = (cfp << 2) | 2ull;  // pending: same-step readers alias row li
-                }
-            }
+        if (do_backup) {
+            // ===== backup site (the only one): MCTS/__init__.py:67-71 ============================================
+            backup_path(arena, path, lane, b_depth, b_int, b_iv, b_fv, vl);
+            ++c_sims;
+            --sims_left;
         }
-        {
-            const size_t pi_ = (size_t)slot * V + inflight;
-            if (lane == 0) {
-                P.pend_own[pi_] = pd.own; P.pend_opp[pi_] = pd.opp; P.pend_legal[pi_] = pd.legal;
-                P.pend_parent[pi_] = pd.parent; P.pend_edge[pi_] = pd.pedge; P.pend_depth[pi_] = pd.depth;
-                P.pend_leaf[pi_] = li;
-                if (vl && pd.parent >= 0) {  // later descents of this wave must not emit the same leaf again
-                    OzNodeHdr* ph = node_at(arena, (u32)pd.parent);
-                    node_child(ph, ph->k)[pd.pedge] = OZ_CH_PENDING;
-                }
-            }
-            u32* pn = P.path_node + pi_ * OZ_MAX_DEPTH;
-            u32* pe = P.path_edge + pi_ * OZ_MAX_DEPTH;
-            if (lane < pd.depth) { pn[lane] = path.n0; pe[lane] = path.e0; }
-            if (lane + 32 < pd.depth) { pn[lane + 32] = path.n1; pe[lane + 32] = path.e1; }
-            __syncwarp();
-        }
-        ++inflight;
-        if (pd.parent < 0) { status = OZ_GAME_WAIT_LEAF; break; }  // the root itself: nothing else can run before it exists
     }
 
     if (lane == 0) {
@@ -723,13 +748,12 @@ __global__ void tree_visits_kernel(const OzTreeParams P, int* __restrict__ visit
     const u64* table = P.table + ((size_t)slot << P.table_log2);
     int player = P.player[slot];
     u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
-    u32 ins;
-    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    const int root = find_ref(table_find(table, P.table_log2, arena, own, opp));
     int v0 = 0, v1 = 0, nsv = 0;
     if (root >= 0) {
-        OzNodeHdr* h = node_at(arena, (u32)root);
+        OzNodeHdr* h = node_at(arena, ref_off(root));
         u64 legal = h->legal;
-        const int* Np = node_N(h, h->k);
+        const int* Np = node_N(h, ref_k(root));
         if ((legal >> lane) & 1ull) v0 = Np[popc(legal & ((1ull << lane) - 1ull))] & N_MASK;
         if ((legal >> (lane + 32)) & 1ull) v1 = Np[popc(legal & ((1ull << (lane + 32)) - 1ull))] & N_MASK;
         nsv = h->ns | (h->vns << 24);  // vns must be 0 whenever no wave is in flight
@@ -746,18 +770,17 @@ __global__ void tree_root_stats_kernel(const OzTreeParams P, int slot, double* _
     const u64* table = P.table + ((size_t)slot << P.table_log2);
     int player = P.player[slot];
     u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
-    u32 ins;
-    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    const int root = find_ref(table_find(table, P.table_log2, arena, own, opp));
     if (lane == 0) *found = root;
     for (int half = 0; half < 2; ++half) {
         int s = lane + 32 * half;
         double qq = 0.0, pp = 0.0;
         int tt = -1;
         if (root >= 0) {
-            OzNodeHdr* h = node_at(arena, (u32)root);
+            OzNodeHdr* h = node_at(arena, ref_off(root));
             if ((h->legal >> s) & 1ull) {
                 int j = popc(h->legal & ((1ull << s) - 1ull));
-                int k = h->k;
+                int k = ref_k(root);
                 qq = node_Q(h, k)[j];
                 pp = node_P(h)[j];
                 int nn = node_N(h, k)[j] & N_MASK;
@@ -778,8 +801,16 @@ int oz_tree_alloc(oz_engine* e) {
     // network while every other game waits for the launch to end (measured: 2 ms tree launches for ~1000 evaluations per
     // step over the last ten plies).  Bounding the run lets the step turn around; per-game results are unchanged (the
     // game resumes at the same simulation in the next launch).
-    P.sim_budget = (e->cfg.prior_mode == OZ_PRIOR_NET || V > 1) ? 8 : 0;  // measured: 4-16 equal, 64 and unbounded slower
+    // Round 2: the count (8 in round 1) became a TIME budget.  In the steady-state mix of game phases a fixed count made the
+    // endgame warps the tail of every launch (ncu: 98 us tree launches against ~30 us in the opening); bounding the launch
+    // by time lets those games use exactly the slack the other warps leave (sweep in DESIGN.md 3d).
+    const bool evaluator = e->cfg.prior_mode == OZ_PRIOR_NET || V > 1;
+    // Wave mode keeps round 1's fixed COUNT: there a yield ends the wave, i.e. it decides which leaves share their virtual
+    // losses, so it must not depend on timing (results stay reproducible and independent of the evaluation cache).
+    P.sim_budget = evaluator ? (V > 1 ? 8 : 64) : 0;
+    P.time_budget = (evaluator && V <= 1) ? 30000 : 0;  // SM clocks (~18 us at 1.65 GHz); 20-40 K measured equal, 5-10 K and 80 K slower
     if (const char* sb = getenv("OZ_TREE_SIM_BUDGET")) P.sim_budget = atoi(sb) > 0 ? atoi(sb) : 0;
+    if (const char* tb = getenv("OZ_TREE_TIME_BUDGET")) P.time_budget = atoll(tb) > 0 ? atoll(tb) : 0;
     e->max_leaves = G * V;
     const size_t GV = (size_t)G * V;
     P.n = e->cfg.board_size;
@@ -797,6 +828,9 @@ int oz_tree_alloc(oz_engine* e) {
     u64 stride = (u64)e->cfg.nodes_per_game * (48 + 24 * 16);
     if (stride < 4096) stride = 4096;
     stride = (stride + 255) & ~255ull;
+    // node references carry the offset (16-byte units) above REF_K_BITS bits of a positive int32
+    OZ_REQUIRE(stride / 16 < (1ull << (31 - REF_K_BITS)), "nodes_per_game %d is too large for 32-bit node references",
+               e->cfg.nodes_per_game);
     e->arena_stride = stride;
     P.arena_stride = stride;
     int rc = 0;
@@ -807,7 +841,7 @@ int oz_tree_alloc(oz_engine* e) {
     A(pend_depth, int, GV) A(pend_leaf, int, GV) A(pend_count, int, G)
     A(path_node, u32, GV * OZ_MAX_DEPTH) A(path_edge, u32, GV * OZ_MAX_DEPTH)
     A(arena, unsigned char, (size_t)G * stride) A(bump, u32, G) A(table, u64, (size_t)G << log2)
-    A(leaf_own, u64, GV) A(leaf_opp, u64, GV) A(leaf_count, int, 4)
+    A(leaf_own, u64, GV) A(leaf_opp, u64, GV) A(leaf_count, int, 8)
     A(counters, u64, 8) A(n_active, int, 4)
     P.next_game = P.n_active + 1;
     P.total_games = 0;
@@ -836,7 +870,9 @@ int oz_tree_alloc(oz_engine* e) {
     OZ_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(u64), e->stream));
     OZ_CUDA(cudaMemsetAsync(P.status, 0, G * sizeof(int), e->stream));
     OZ_CUDA(cudaMemsetAsync(P.pend_count, 0, G * sizeof(int), e->stream));
-    OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, 4 * sizeof(int), e->stream));
+    OZ_CUDA(cudaMemsetAsync(P.leaf_count, 0, 8 * sizeof(int), e->stream));
+    e->leaf_count_base = P.leaf_count;
+    P.leaf_count_next = nullptr;
     OZ_CUDA(cudaMemsetAsync(P.n_active, 0, 4 * sizeof(int), e->stream));
     return OZ_OK;
 }
@@ -905,8 +941,7 @@ __global__ void tree_find_roots_kernel(const OzTreeParams P) {
     const u64* table = P.table + ((size_t)slot << P.table_log2);
     int player = P.player[slot];
     u64 own = player ? P.white[slot] : P.black[slot], opp = player ? P.black[slot] : P.white[slot];
-    u32 ins;
-    int root = table_find(table, P.table_log2, arena, own, opp, lane, &ins);
+    const int root = find_ref(table_find(table, P.table_log2, arena, own, opp));
     if (lane == 0) P.root_node[slot] = root;
 }
 
@@ -971,15 +1006,6 @@ int oz_tree_visits(oz_engine* e, int* visits_dev, int* ns_dev) {
 int oz_tree_root_stats(oz_engine* e, int game, double* q_dev, double* p_dev, int* tag_dev) {
     OzTreeParams& P = e->tp;
     tree_root_stats_kernel<<<1, 32, 0, e->stream>>>(P, game, q_dev, p_dev, tag_dev, tag_dev + 64);
-    OZ_CUDA(cudaGetLastError());
-    e->launches++;
-    return OZ_OK;
-}
-
-int oz_tree_cache_publish(oz_engine* e) {
-    OzTreeParams& P = e->tp;
-    if (!P.cache_tags) return OZ_OK;
-    cache_publish_kernel<<<(P.G * P.vl_width + 7) / 8, 256, 0, e->stream>>>(P);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
     return OZ_OK;
