@@ -197,24 +197,11 @@ def synthetic_starts(engine_mod, n_games, seed, first_id, device, spread=8):
     return b, w, p
 
 
-def l2_bandwidth(torch, device, mb=24, reps=60):
-    """Measured L2 bandwidth on this GPU: a 24 MB buffer (L2-resident: B200 has 126 MB) read by torch.sum, and copied
-    (read + write) by Tensor.copy_, timed with CUDA events.  The denominator of the table gather's roofline."""
-    x = torch.empty(mb << 18, dtype=torch.float32, device=device).normal_()
-    y = torch.empty_like(x)
-    out = {}
-    for name, fn, nbytes in (("read", lambda: x.sum(), x.numel() * 4), ("copy", lambda: y.copy_(x), x.numel() * 8)):
-        for _ in range(5):
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        out[name + "_gbs"] = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
-    out["what"] = f"{mb} MB L2-resident buffer, torch.sum (read) / Tensor.copy_ (read+write), {reps} launches each"
-    return out
+def l2_bandwidth(E, device, mb=32, passes=50):
+    """Measured L2 read bandwidth on this GPU (oz_probe_l2_read: streaming 16-byte loads over a 32 MB L2-resident buffer,
+    CUDA events) - the denominator of the table gather's roofline."""
+    best = max(E.probe_l2_read(mb, passes, device) for _ in range(3))
+    return {"read_gbs": best, "what": f"oz_probe_l2_read: {passes} sweeps of 16-byte .cg loads over a {mb} MB L2-resident buffer, best of 3"}
 
 
 class Ctx:
@@ -344,7 +331,7 @@ def tensor_roofline(cx, leg, C, conv2, conv3, peaks):
         l2 = cx.l2
         gather = {"bound": "l2", "kernel": "conv2_table_gather_kernel (conv1+conv2 as 484 table-row reads per board)",
                   "achieved": gb, "peak": l2["read_gbs"], "unit": "GB/s", "frac": gb / l2["read_gbs"],
-                  "peak_source": "measured in this run: " + l2["what"], "l2_copy_gbs": l2["copy_gbs"],
+                  "peak_source": "measured in this run: " + l2["what"],
                   "avg_launch_ms": float(lt[1]),
                   "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_final_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
                   "note": "achieved = ALGORITHMIC row bytes (548 KB per board) / launch time; the rows are served by L1 (ncu: 57 % "
@@ -403,7 +390,7 @@ def run_ours(args):
         if world > 1:
             dist.broadcast(cx.wt, src=0)
         torch.cuda.synchronize()
-        cx.l2 = l2_bandwidth(torch, f"cuda:{local}")
+        cx.l2 = l2_bandwidth(E, local)
     tree_only = mode == E.PRIOR_HASH
     leg = selfplay_leg(cx, games=G, sims=sims, vl=args.vl, cache_log2=args.eval_cache_log2, window=args.window,
                        steps=args.steps, warmup=args.warmup, mode=mode)

@@ -208,6 +208,31 @@ int oz_engine_launches(oz_engine* e, uint64_t* launches);
 int oz_net_set_timing(oz_engine* e, int32_t on);
 int oz_net_layer_times(oz_engine* e, float* ms8);
 
+/* ---- dist: the two collectives of an iteration, over NCCL (one process per GPU) ---------------------- */
+/* C1 replaces the reference's weight fan-out (workers.py:203-296: temp .h5 -> sftp -> scp tree), C2 its result gather
+ * (pickled stdout, workers.py:147-159,180-184).  Nothing is exchanged while games are played (they shard by id).
+ * NCCL is resolved at run time (dlopen libnccl.so.2); without it these calls fail with OZ_ERR_STATE.
+ * oz_dist_unique_id: rank 0 creates the 128-byte ncclUniqueId, the host ships it to the other ranks (any channel);
+ * oz_dist_init: every rank joins (collective; the communicator lives on the engine's device and stream). */
+int oz_dist_unique_id(uint8_t* id128);
+int oz_dist_init(oz_engine* e, int32_t rank, int32_t world, const uint8_t* id128);
+int oz_dist_destroy(oz_engine* e);
+/* C1 (collective): `root` passes the float32 HOST blob (oz_net_load_weights' format), the others may pass NULL; every rank
+ * ends with the weights folded and loaded on its device (and its evaluation cache cleared). */
+int oz_dist_broadcast_weights(oz_engine* e, const float* blob, int64_t n_floats, int32_t channels, int32_t root);
+/* C2 (collective): every rank contributes n_rows packed example rows (3 x uint64 per position: black, white,
+ * action | player<<8 | winner<<16 | game<<32 - othellozero_b200.dist.pack_records) from a HOST buffer and receives the
+ * concatenation in rank order in out_rows (HOST, capacity_rows rows); *total_rows = rows gathered.  out_rows = NULL only
+ * queries the total (still collective). */
+int oz_dist_gather_examples(oz_engine* e, const uint64_t* rows, int64_t n_rows, uint64_t* out_rows, int64_t capacity_rows,
+                            int64_t* total_rows);
+
+/* ---- measurement aid (bench.py) ---------------------------------------------------------------------- */
+/* L2 read bandwidth of `device`, GB/s: `passes` sweeps of 16-byte loads over an L2-resident buffer of `megabytes` MB
+ * (B200: 126 MB of L2), timed with CUDA events.  The denominator of the conv1∘conv2 table gather's roofline: that kernel
+ * is bound by the L2 -> SM path, not by HBM.  (No reference counterpart: the reference has no kernels to measure.) */
+int oz_probe_l2_read(int32_t device, int32_t megabytes, int32_t passes, double* gb_per_s);
+
 #ifdef __cplusplus
 }
 #endif

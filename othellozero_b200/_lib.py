@@ -70,6 +70,12 @@ SIGNATURES = {
     "oz_engine_launches": (C.c_int, [vp, u64p]),
     "oz_net_layer_times": (C.c_int, [vp, f32p]),
     "oz_net_set_timing": (C.c_int, [vp, C.c_int32]),
+    "oz_probe_l2_read": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, f64p]),
+    "oz_dist_unique_id": (C.c_int, [u8p]),
+    "oz_dist_init": (C.c_int, [vp, C.c_int32, C.c_int32, u8p]),
+    "oz_dist_destroy": (C.c_int, [vp]),
+    "oz_dist_broadcast_weights": (C.c_int, [vp, f32p, C.c_int64, C.c_int32, C.c_int32]),
+    "oz_dist_gather_examples": (C.c_int, [vp, u64p, C.c_int64, u64p, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liboz_b200.so")
-SOURCES = ["oz_rules.cu", "oz_tree.cu", "oz_net.cu", "oz_capi.cu"]
+SOURCES = ["oz_rules.cu", "oz_tree.cu", "oz_net.cu", "oz_capi.cu", "oz_dist.cu"]
 
 
 def nvcc_path() -> str:
@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", SO] + SOURCES
+           "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-o", SO] + SOURCES + ["-ldl"]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     subprocess.check_call(cmd, cwd=CSRC)

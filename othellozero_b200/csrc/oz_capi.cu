@@ -111,6 +111,7 @@ extern "C" int oz_engine_destroy(oz_engine* e) {
     if (!e) return OZ_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    oz_dist_destroy(e);
     oz_net_destroy(e);
     for (int i = 0; i < e->n_allocs; ++i) cudaFree(e->allocs[i]);
     if (e->rec_buf) cudaFree(e->rec_buf);

@@ -128,6 +128,8 @@ struct oz_engine {
     int* leaf_count_base = nullptr;  // [8]: [0] leaf count, [1] net-forward count, [2] waiting games, [3] bad start, [4] second leaf count (self-play ping-pong)
     OzNet* net = nullptr;
     float layer_ms[8] = {0};
+    void* comm = nullptr;      // ncclComm_t of oz_dist_init (oz_dist.cu), or null
+    int dist_rank = 0, dist_world = 1;
 };
 
 // tree (oz_tree.cu)

@@ -295,3 +295,50 @@ extern "C" int oz_perft_playouts_host(int32_t device, int32_t board_size, uint64
     if (moves) memcpy(moves, S.pin + 2 * b8 + b4, (size_t)n_games * 64);
     return OZ_OK;
 }
+
+
+// ---- measurement aid: L2 read bandwidth ---------------------------------------------------------------------------------
+// The table gather (oz_net.cu) is bound by the L2 -> SM path, so bench.py states its roofline against the L2 read
+// bandwidth MEASURED on the box: every thread streams 16-byte loads (8 independent ones in flight) over an L2-resident
+// buffer; the XOR of what it read is stored only if it matches a value it cannot have, which keeps the loads alive.
+__global__ void __launch_bounds__(256) l2_read_probe_kernel(const uint4* __restrict__ buf, size_t n16, int passes, unsigned* sink) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int p = 0; p < passes; ++p) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n16; i += 8 * stride) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(buf + i + u * stride);  // .cg: L2 only, like a table row's first touch
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc.x ^= v[u].x; acc.y ^= v[u].y; acc.z ^= v[u].z; acc.w ^= v[u].w; }
+        }
+        for (; i < n16; i += stride) { const uint4 v = __ldcg(buf + i); acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w; }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9E3779B9u && passes < 0) *sink = acc.x;
+}
+
+extern "C" int oz_probe_l2_read(int32_t device, int32_t megabytes, int32_t passes, double* gb_per_s) {
+    OZ_REQUIRE(gb_per_s && megabytes >= 1 && megabytes <= 4096 && passes >= 1, "bad argument");
+    OZ_CUDA(cudaSetDevice(device));
+    const size_t bytes = (size_t)megabytes << 20, n16 = bytes / 16;
+    unsigned char* buf = nullptr;
+    OZ_CUDA(cudaMalloc((void**)&buf, bytes + 16));
+    struct Guard { void* p; cudaEvent_t a = nullptr, b = nullptr; ~Guard() { cudaFree(p); if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } g{buf};
+    OZ_CUDA(cudaMemset(buf, 0x5A, bytes + 16));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    OZ_CUDA(cudaEventCreate(&g.a));
+    OZ_CUDA(cudaEventCreate(&g.b));
+    unsigned* sink = (unsigned*)(buf + bytes);
+    l2_read_probe_kernel<<<sms * 8, 256>>>((const uint4*)buf, n16, 2, sink);  // warm: brings the buffer into L2
+    OZ_CUDA(cudaEventRecord(g.a));
+    l2_read_probe_kernel<<<sms * 8, 256>>>((const uint4*)buf, n16, passes, sink);
+    OZ_CUDA(cudaEventRecord(g.b));
+    OZ_CUDA(cudaEventSynchronize(g.b));
+    OZ_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    OZ_CUDA(cudaEventElapsedTime(&ms, g.a, g.b));
+    *gb_per_s = (double)bytes * passes / (ms * 1e-3) / 1e9;
+    return OZ_OK;
+}

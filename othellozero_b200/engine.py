@@ -68,6 +68,13 @@ def perft_playouts(n_games: int, board_size: int = 8, seed: int = 0, first_game_
                 passes=(info >> 16).astype(np.int32), moves=moves)
 
 
+def probe_l2_read(megabytes: int = 32, passes: int = 50, device: int = 0) -> float:
+    """Measured L2 read bandwidth in GB/s (oz_probe_l2_read): the table gather's roofline denominator."""
+    out = C.c_double(0.0)
+    check(_lib.load().oz_probe_l2_read(device, megabytes, passes, C.byref(out)))
+    return float(out.value)
+
+
 class Engine:
     """oz_engine handle: node pools + per-game state for `max_games` concurrent games on one GPU."""
 
@@ -238,6 +245,36 @@ class Engine:
         """float32 CUDA tensor (e.g. just received by an NCCL broadcast) -> fold + cast on device."""
         assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 4 and t.is_contiguous()
         self.load_weights_dev(t.data_ptr(), t.numel(), channels)
+
+    # -- dist (NCCL through the C-ABI, oz_dist.cu) ---------------------------------------------------------------
+    @staticmethod
+    def dist_unique_id() -> bytes:
+        """Rank 0: the 128-byte NCCL id to ship to the other ranks (any channel: a pipe, a file, torch.distributed)."""
+        buf = np.zeros(128, dtype=np.uint8)
+        check(_lib.load().oz_dist_unique_id(ptr(buf, u8p)))
+        return buf.tobytes()
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+        assert buf.size == 128
+        check(self._L.oz_dist_init(self._h, rank, world, ptr(buf, u8p)))
+
+    def dist_broadcast_weights(self, blob, channels: int, root: int = 0):
+        """C1: `root` passes the float32 blob, the others None; every rank ends with the weights loaded."""
+        blob = None if blob is None else np.ascontiguousarray(blob, dtype=np.float32)
+        n = int(self._L.oz_net_blob_floats(self.board_size, channels))
+        check(self._L.oz_dist_broadcast_weights(self._h, ptr(blob, f32p), n, channels, root))
+
+    def dist_gather_examples(self, rows: np.ndarray) -> np.ndarray:
+        """C2: packed example rows [n, 3] uint64 of this rank -> the concatenation over all ranks, in rank order."""
+        rows = np.ascontiguousarray(rows, dtype=np.uint64).reshape(-1, 3)
+        total = C.c_int64(0)
+        check(self._L.oz_dist_gather_examples(self._h, ptr(rows, u64p) if rows.size else None, rows.shape[0], None, 0,
+                                              C.byref(total)))
+        out = np.zeros((int(total.value), 3), dtype=np.uint64)
+        check(self._L.oz_dist_gather_examples(self._h, ptr(rows, u64p) if rows.size else None, rows.shape[0],
+                                              ptr(out, u64p) if out.size else None, out.shape[0], C.byref(total)))
+        return out
 
     def layer_times(self):
         ms = np.zeros(8, dtype=np.float32)

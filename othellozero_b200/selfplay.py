@@ -45,7 +45,8 @@ class SelfPlay:
     """A pool of concurrent self-play games on one GPU (one warp per game)."""
 
     def __init__(self, board_size: int, neural_network, degree_exploration: float = 1.0, max_games: int = 4096,
-                 num_simulations: int = 100, device: int = 0, seed: int = 0, log_visits: bool = False):
+                 num_simulations: int = 100, device: int = 0, seed: int = 0, log_visits: bool = False,
+                 eval_cache_log2: int = 22):
         self.board_size = board_size
         self.num_simulations = num_simulations
         if isinstance(neural_network, HashPriorNet):
@@ -57,7 +58,10 @@ class SelfPlay:
                             "othellozero_b200.mcts.OthelloMCTS (host-evaluated priors)")
         self.engine = _e.Engine(board_size, max_games=max_games,
                                 nodes_per_game=default_nodes_per_game(board_size, num_simulations), prior_mode=mode,
-                                c_puct=float(degree_exploration), seed=seed, device=device, log_visits=log_visits)
+                                c_puct=float(degree_exploration), seed=seed, device=device, log_visits=log_visits,
+                                # identical positions reached by different games are evaluated once (results unchanged:
+                                # tests/test_gpu_net.py::test_eval_cache_is_results_preserving); 272 B per entry
+                                eval_cache_log2=eval_cache_log2 if mode == _e.PRIOR_NET else 0)
         if mode == _e.PRIOR_NET:
             self.engine.load_weights(neural_network.blob, neural_network.channels)
 

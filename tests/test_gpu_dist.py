@@ -81,3 +81,55 @@ def test_iteration_driver_runs_end_to_end():
         assert 0 <= d["arena_new_wins"] <= 6 and d["selfplay_sims"] == 10 * d["positions_gathered"]
         assert np.isfinite(np.array(d["train_history"])).all()
     assert lines[1]["buffer_examples"] >= lines[0]["buffer_examples"]
+
+
+# ---- C1 / C2 through the C-ABI (oz_dist.cu, NCCL) ------------------------------------------------------------------------
+def _cabi_rank(rank, world, uid_q, out_q):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    from othellozero_b200 import engine as E, net as oznet
+    n, C = 6, 128
+    e = E.Engine(n, max_games=8, nodes_per_game=2, prior_mode=E.PRIOR_NET, device=rank)
+    if rank == 0:
+        uid = E.Engine.dist_unique_id()
+        for _ in range(world - 1):
+            uid_q.put(uid)
+    else:
+        uid = uid_q.get(timeout=120)
+    e.dist_init(rank, world, uid)
+    blob = oznet.init_weights(n, C, seed=13, randomize_bn=True) if rank == 0 else None
+    e.dist_broadcast_weights(blob, C, root=0)                              # C1
+    own, opp = np.array([0x0000000810000000], dtype=np.uint64), np.array([0x0000001008000000], dtype=np.uint64)
+    pi, lg, v = e.net_forward(own, opp)
+    rows = (np.arange(3 * (2 + 3 * rank), dtype=np.uint64).reshape(-1, 3) + np.uint64(1000 * rank))
+    allrows = e.dist_gather_examples(rows)                                 # C2
+    empty = e.dist_gather_examples(np.zeros((0, 3), dtype=np.uint64) if rank else rows[:1])
+    out_q.put((rank, lg.copy(), float(v[0]), allrows, empty))
+    e.close()
+
+
+def test_c_abi_broadcast_and_gather_over_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("NCCL needs one GPU per rank (run with gpurun --gpus 2)")
+    from othellozero_b200 import engine as E, net as oznet
+    ctx = mp.get_context("spawn")
+    uid_q, out_q = ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_cabi_rank, args=(r, 2, uid_q, out_q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted((out_q.get(timeout=600) for _ in ps), key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    # C1: both ranks evaluate with rank 0's weights - bit-identical to a local load of the same blob
+    e = E.Engine(6, max_games=8, nodes_per_game=2, prior_mode=E.PRIOR_NET)
+    e.load_weights(oznet.init_weights(6, 128, seed=13, randomize_bn=True), 128)
+    _, lg, v = e.net_forward(np.array([0x0000000810000000], dtype=np.uint64), np.array([0x0000001008000000], dtype=np.uint64))
+    e.close()
+    for rank, rlg, rv, allrows, empty in res:
+        assert np.array_equal(rlg, lg) and rv == float(v[0])
+        # C2: concatenation in rank order
+        exp = np.concatenate([np.arange(6, dtype=np.uint64).reshape(-1, 3), np.arange(15, dtype=np.uint64).reshape(-1, 3) + np.uint64(1000)])
+        assert np.array_equal(allrows, exp)
+        assert empty.shape == (1, 3) and np.array_equal(empty[0], [0, 1, 2])       # a rank may contribute nothing
