@@ -427,8 +427,9 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             for (int j = 0; j < 64; j += 4)
                                 *reinterpret_cast<float4*>(crow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
                             p.cache_v[cidx] = val;
-                            __threadfence();
-                            atomicOr(p.cache_tags + cidx, 1ull);  // pending (2) -> ready (3): fire and forget, no read round trip
+                            // pending (2) -> ready (3): fire and forget.  No fence: nobody reads an entry's priors during this
+                            // kernel (same-step readers share the leaf row), later kernels are ordered by the stream
+                            atomicOr(p.cache_tags + cidx, 1ull);
                         }
                     }
                 }
@@ -684,6 +685,292 @@ oz_gemm2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    }
+    trace_end(p.trace);
+}
+
+// ---- fc2 + heads in ONE kernel (opt-in, OZ_NET_TAIL=fused; a measured negative result) --------------------------
+// fc2 (4 GFLOP) and the heads (0.5 GFLOP) run as two launches of the generic kernels: 20 + 25 us per 3800 boards for 3 us of
+// tensor work.  This kernel lets one CTA own 128 batch rows end to end:
+//   fc2    f2[128 x 512] = relu(f1[128 x 1024] . W4'^T + b4')   two N = 256 halves, 16 k-blocks each, accumulators in TMEM
+//                                                               columns [0,256) and [256,512)
+//   drain  each half goes TMEM -> +bias, ReLU, bf16 -> SHARED MEMORY in the K-major 128-byte-swizzled layout tcgen05.mma
+//          reads its A operand from (and to global f2, kept for inspection)
+//   heads  logits[128 x 128] = f2 . W5^T: A = the f2 tile just written, B = the head weights streamed through the same TMA
+//          ring; 4 k-blocks per f2 half, accumulated in TMEM columns [0,128) (free again once half 0 is drained)
+//   epilogue = the heads epilogue of oz_gemm_kernel (softmax, tanh, evaluation-cache publish)
+// Bit-identical to the two launches (tests/test_gpu_net.py::test_fused_tail_matches_split_launches), but NOT faster: with 128-row
+// tiles only 32 CTAs exist at 4096 boards, each pulling 48 KB per k-block through a 3-deep ring (8 us per half against 4 us of
+// MMA time), the drains cost 5 us each and the one-thread-per-row heads epilogue 7 us: 30 us after fc1 ends against 24 us for the
+// two launches (whose prologues hide under their predecessors thanks to PDL).  The per-phase %globaltimer stamps (p.dbg) are
+// what established this.
+constexpr int TSTAGES = 3;
+constexpr int T_B_STAGE_BYTES = 256 * BLOCK_K * 2;  // fc2: 256 weight rows per k-block; the heads use the first 16 KB
+struct TailSmem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_B = TSTAGES * A_STAGE_BYTES;
+    static constexpr int OFF_F2 = OFF_B + TSTAGES * T_B_STAGE_BYTES;  // one f2 half: 4 k-blocks x [128 rows x 128 B]
+    static constexpr int OFF_BAR = OFF_F2 + 4 * A_STAGE_BYTES;         // full[S], empty[S], tfull[3], f2ready[2], hdone, tfree
+    static constexpr int OFF_TMEM = OFF_BAR + (2 * TSTAGES + 7) * 8 + 8;
+    static constexpr int OFF_BIAS = OFF_TMEM + 16;                     // [512] fc2 + [128] heads
+    static constexpr int BYTES = OFF_BIAS + 640 * 4;
+    static constexpr int DYN_BYTES = BYTES + 1024;
+};
+struct TailParams {
+    int max_count;
+    const int* count;
+    const float* bias4; const float* bias5;
+    bf16* f2;                              // [B][512], written for inspection (oz_net_get_activation)
+    float* pi; float* logits; float* v;
+    int nsq;
+    const int* cache_idx; float* cache_pi; float* cache_v; unsigned long long* cache_tags;  // see GemmParams
+    unsigned long long* trace;
+    unsigned long long* dbg;  // OZ_NET_TRACE: 8 %globaltimer stamps of CTA 0 (pdl wait over, tfull0, f2ready0, tfull1, f2ready1, tfull2, logits read, done)
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+oz_tail_kernel(const __grid_constant__ CUtensorMap mapA /* f1: (1024, 1, 1, B), box (64, 1, 1, 128) */,
+               const __grid_constant__ CUtensorMap mapB4 /* W4': (1024, 512), box (64, 256) */,
+               const __grid_constant__ CUtensorMap mapB5 /* W5: (512, 128), box (64, 128) */, const TailParams p) {
+    using S = TailSmem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - raw);
+    const uint32_t sA = base + S::OFF_A, sB = base + S::OFF_B, sF2 = base + S::OFF_F2, sBar = base + S::OFF_BAR;
+    auto full_bar = [&](int s) { return sBar + 8u * s; };
+    auto empty_bar = [&](int s) { return sBar + 8u * (TSTAGES + s); };
+    auto tfull_bar = [&](int a) { return sBar + 8u * (2 * TSTAGES + a); };        // fc2 half 0, half 1, heads
+    auto f2ready_bar = [&](int h) { return sBar + 8u * (2 * TSTAGES + 3 + h); };  // f2 half h is in shared memory
+    const uint32_t hdone_bar = sBar + 8u * (2 * TSTAGES + 5);                      // heads MMAs over half 0 retired
+    const uint32_t tfree_bar = sBar + 8u * (2 * TSTAGES + 6);                      // heads accumulator read out
+    volatile uint32_t* s_tmem = (volatile uint32_t*)(gbase + S::OFF_TMEM);
+    float* s_bias = (float*)(gbase + S::OFF_BIAS);
+    uint8_t* f2buf = gbase + S::OFF_F2;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    trace_begin(p.trace);
+    int L = *p.count;
+    if (L > p.max_count) L = p.max_count;
+    const int num_tiles = (L + BLOCK_M - 1) / BLOCK_M;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB4);
+        tma_prefetch_desc(&mapB5);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 3; ++a) mbar_init(tfull_bar(a), 1);
+        mbar_init(f2ready_bar(0), 4); mbar_init(f2ready_bar(1), 4);  // one arrive per epilogue warp
+        mbar_init(hdone_bar, 1);
+        mbar_init(tfree_bar, 4);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32((const void*)s_tmem), 512);
+        tmem_relinquish();
+    }
+    if (warp >= 4) {  // weights, not activations: may be read before the previous layer has finished
+        const int et = threadIdx.x - 128;
+        for (int i = et; i < 512; i += 128) s_bias[i] = p.bias4[i];
+        s_bias[512 + et] = p.bias5[et];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===== TMA producer: 2 x 16 stages of (f1 k-block, 256 fc2 weight rows), then 8 stages of head weights =====
+        pdl_wait();  // f1 is the previous kernel's output
+        if (p.dbg && blockIdx.x == 0 && lane == 0) p.dbg[0] = global_ns();
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int row0 = tile * BLOCK_M;
+            for (int h = 0; h < 2; ++h) {
+                for (int kc = 0; kc < 1024; kc += BLOCK_K) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    if (elect_one()) {
+                        const uint32_t fb = full_bar(stage);
+                        mbar_expect_tx(fb, (uint32_t)(A_STAGE_BYTES + T_B_STAGE_BYTES));
+                        tma_load_4d(sA + stage * A_STAGE_BYTES, &mapA, fb, kc, 0, 0, row0);
+                        tma_load_2d(sB + stage * T_B_STAGE_BYTES, &mapB4, fb, kc, h * 256);
+                    }
+                    __syncwarp();
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+            for (int kc = 0; kc < 512; kc += BLOCK_K) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t fb = full_bar(stage);
+                    mbar_expect_tx(fb, (uint32_t)A_STAGE_BYTES);  // 128 rows x 64 k of W5
+                    tma_load_2d(sB + stage * T_B_STAGE_BYTES, &mapB5, fb, kc, 0);
+                }
+                __syncwarp();
+                if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (converged warp, elected lane) =====
+        constexpr uint32_t idesc_fc2 = make_idesc(BLOCK_M, 256);
+        constexpr uint32_t idesc_heads = make_idesc(BLOCK_M, 128);
+        const uint32_t a_lo0 = sw128_desc_lo(sA), b_lo0 = sw128_desc_lo(sB), f_lo0 = sw128_desc_lo(sF2);
+        int stage = 0; uint32_t phase = 0;
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it ^= 1u) {
+            mbar_wait(tfree_bar, it ^ 1u);  // the previous tile's logits have left TMEM columns [0,128)
+            tc_fence_after();
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(h * 256);
+                for (int kb = 0; kb < 16; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (T_B_STAGE_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_lo(d_tmem, a_lo + 2u * k, b_lo + 2u * k, idesc_fc2, (kb | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));
+                    }
+                    __syncwarp();
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (elect_one()) umma_commit(tfull_bar(h));
+                __syncwarp();
+            }
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(f2ready_bar(h), it);  // f2 half h sits in shared memory (and, h = 0: columns [0,256) are drained)
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = f_lo0 + (uint32_t)kb * (A_STAGE_BYTES >> 4);
+                    const uint32_t b_lo = b_lo0 + (uint32_t)stage * (T_B_STAGE_BYTES >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                            umma_bf16_lo(tmem_base, a_lo + 2u * k, b_lo + 2u * k, idesc_heads, (h | kb | k) ? 1u : 0u);
+                        umma_commit(empty_bar(stage));
+                    }
+                    __syncwarp();
+                    if (++stage == TSTAGES) { stage = 0; phase ^= 1u; }
+                }
+                if (elect_one()) umma_commit(h == 0 ? hdone_bar : tfull_bar(2));
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue warps: drain fc2 halves into the heads' A operand, then the heads epilogue =====
+        const int ew = warp - 4;
+        const int r = ew * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(ew * 32) << 16);
+        uint8_t* f2row = f2buf + (r >> 3) * 1024 + (r & 7) * 128;
+        const uint32_t sw = (uint32_t)(r & 7);
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it ^= 1u) {
+            const long long grow = (long long)tile * BLOCK_M + r;
+            const bool ok = grow < (long long)L;
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(tfull_bar(h), it);
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[1 + 2 * h] = global_ns();
+                if (h == 1) mbar_wait(hdone_bar, it);  // the heads MMAs have finished reading half 0 out of the buffer
+                tc_fence_after();
+                const float* bias = s_bias + h * 256;
+                bf16* grow_out = p.f2 + grow * 512 + h * 256;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(t_lane + (uint32_t)(h * 256 + c * 32), v);
+                    tmem_ld_wait();
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 bj = *reinterpret_cast<const float2*>(bias + c * 32 + 2 * j);
+                        const float2 y = __fadd2_rn(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), bj);
+                        packed[j] = pack_relu_bf16x2(y.x, y.y);
+                    }
+                    // columns c*32 .. c*32+31 of this half = k-block c/2, 16-byte chunks (c&1)*4 .. +3 of the 128-byte row,
+                    // stored where the 128B swizzle (chunk ^ (row & 7)) puts them
+                    uint8_t* kb_row = f2row + (c >> 1) * A_STAGE_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint4 val = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                        const uint32_t ch = (uint32_t)((c & 1) * 4 + q);
+                        *reinterpret_cast<uint4*>(kb_row + ((ch ^ sw) << 4)) = val;
+                        if (ok) *reinterpret_cast<uint4*>(grow_out + c * 32 + q * 8) = val;
+                    }
+                }
+                fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's reads
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(f2ready_bar(h));
+                if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[2 + 2 * h] = global_ns();
+            }
+            // heads: columns [0,nsq) = policy logits, column nsq = value pre-activation (same code as oz_gemm_kernel<128, EPI_HEADS>)
+            mbar_wait(tfull_bar(2), it);
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[5] = global_ns();
+            tc_fence_after();
+            const float* bias = s_bias + 512;
+            float lg[96];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t v[32];
+                tmem_ld32(t_lane + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) lg[c * 32 + j] = __uint_as_float(v[j]) + bias[c * 32 + j];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tfree_bar);  // the logits are in registers: the next tile may overwrite the accumulator
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[6] = global_ns();
+            if (ok) {
+                const int nsq = p.nsq;
+                float mx = -3.0e38f;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) if (j < nsq) mx = fmaxf(mx, lg[j]);
+                float sum = 0.f;
+                float ex[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) { ex[j] = (j < nsq) ? expf(lg[j] - mx) : 0.f; sum += ex[j]; }
+                const float inv = 1.0f / sum;
+                float* lrow = p.logits + grow * 64;
+                float* prow = p.pi + grow * 64;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                    *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
+                    *reinterpret_cast<float4*>(prow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                }
+                const float val = tanhf(nsq == 64 ? lg[64] : lg[36]);
+                p.v[grow] = val;
+                if (p.cache_idx) {
+                    const int cidx = p.cache_idx[grow];
+                    if (cidx >= 0) {
+                        float* crow = p.cache_pi + (size_t)cidx * 64;
+#pragma unroll
+                        for (int j = 0; j < 64; j += 4)
+                            *reinterpret_cast<float4*>(crow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                        p.cache_v[cidx] = val;
+                        atomicOr(p.cache_tags + cidx, 1ull);  // no fence needed: see oz_gemm_kernel's heads epilogue
+                    }
+                }
+            }
+            if (p.dbg && blockIdx.x == 0 && threadIdx.x == 128) p.dbg[7] = global_ns();
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
     }
     trace_end(p.trace);
 }
@@ -1278,6 +1565,7 @@ struct OzNet {
     OzLayer tbl;
     // conv3 as 1-D Winograd F(2,3): OZ_NET_CONV3=wino (needs conv2_table: the gather emits the input transform)
     bool conv3_wino = false;
+    bool fused_tail = false;  // OZ_NET_TAIL=fused: fc2 + heads as oz_tail_kernel (a measured negative result)
     bf16* v3 = nullptr;      // [4][Bmax][T][n][C]
     bf16* u3 = nullptr;      // [4][C][3C]
     CUtensorMap mapV, mapU;
@@ -1343,6 +1631,8 @@ int oz_net_create(oz_engine* e) {
     net->conv2_table = !(c2 && c2[0] == 'g');
     const char* c3 = getenv("OZ_NET_CONV3");
     net->conv3_wino = net->conv2_table && c3 && c3[0] == 'w';  // opt-in: measured at parity with the direct kernel
+    const char* tl = getenv("OZ_NET_TAIL");
+    net->fused_tail = tl && tl[0] == 'f';  // opt-in: measured slower than the two generic launches
     const char* tr = getenv("OZ_NET_TRACE");
     if (tr && atoi(tr) > 0) net->trace_slots = atoi(tr) > 256 ? 256 : atoi(tr);
     const char* te = getenv("OZ_NET_TIMING_EVERY");
@@ -1558,6 +1848,7 @@ int oz_net_load(oz_engine* e, const float* blob, int64_t n_floats, int channels,
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<128, EPI_RELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      GemmSmem<128>::DYN_BYTES));
         OZ_CUDA(cudaFuncSetAttribute(oz_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem::DYN_BYTES));
+        OZ_CUDA(cudaFuncSetAttribute(oz_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailSmem::DYN_BYTES));
         OZ_CUDA(cudaMemsetAsync(net->w[5], 0, 128ull * 512 * 2, st));
         OZ_CUDA(cudaMemsetAsync(net->bias[5], 0, 128 * 4, st));
     }
@@ -1696,7 +1987,11 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         p.count = count_dev;
         p.max_count = max_count;
         static const char* lname[6] = {"conv2", "conv3", "conv4", "fc1", "fc2", "heads"};
-        p.trace = trace_slot(net, lname[li]);
+        if (li == 5 && net->fused_tail) {  // the heads ran inside the fc2 launch
+            if (tm) cudaEventRecord(ev[2 + li], st);
+            continue;
+        }
+        p.trace = (li == 4 && net->fused_tail) ? nullptr : trace_slot(net, lname[li]);
         p.pi = pi_dev; p.logits = logits_dev; p.v = v_dev;
         if (publish && li == 5) {
             p.cache_idx = e->tp.leaf_cache_idx; p.cache_pi = e->tp.cache_pi; p.cache_v = e->tp.cache_v;
@@ -1714,7 +2009,27 @@ int oz_net_forward(oz_engine* e, const u64* own_dev, const u64* opp_dev, const i
         cfg.attrs = attr;
         cfg.numAttrs = net->pdl ? 1 : 0;
         cudaError_t lerr;
-        if (li == 1 && net->conv3_wino) {
+        if (li == 4 && net->fused_tail) {
+            TailParams tp{};
+            tp.max_count = max_count;
+            tp.count = count_dev;
+            tp.bias4 = net->bias[4]; tp.bias5 = net->bias[5];
+            tp.f2 = net->f2;
+            tp.pi = pi_dev; tp.logits = logits_dev; tp.v = v_dev;
+            tp.nsq = nsq;
+            if (publish) {
+                tp.cache_idx = e->tp.leaf_cache_idx; tp.cache_pi = e->tp.cache_pi; tp.cache_v = e->tp.cache_v;
+                tp.cache_tags = e->tp.cache_tags;
+            }
+            tp.trace = trace_slot(net, "fc2+heads");
+            if (tp.trace && net->trace_next + 4 <= net->trace_slots) {  // 4 more slots = 8 stamps of CTA 0
+                tp.dbg = trace_slot(net, "t:w,f0"); trace_slot(net, "t:r0,f1"); trace_slot(net, "t:r1,f2"); trace_slot(net, "t:lg,end");
+            }
+            const int m_tiles = (max_count + BLOCK_M - 1) / BLOCK_M;
+            cfg.gridDim = dim3(m_tiles < net->sm_count ? (m_tiles < 1 ? 1 : m_tiles) : net->sm_count);
+            cfg.dynamicSmemBytes = TailSmem::DYN_BYTES;
+            lerr = cudaLaunchKernelEx(&cfg, oz_tail_kernel, Lr.mapA, Lr.mapB, net->layer[5].mapB, tp);
+        } else if (li == 1 && net->conv3_wino) {
             WinoParams wp = net->wp;
             wp.count = count_dev;
             wp.max_count = max_count;

@@ -341,13 +341,63 @@ __device__ __forceinline__ int cache_probe(const OzTreeParams& P, u64 own, u64 o
 }
 
 // Publishing (copying an owner's priors into its entry and marking it ready) is the heads kernel's epilogue: oz_net.cu.
+
+// Warp arg-max of (u, j): largest u, ties -> smallest j (the reference's first-max, MCTS/__init__.py:65); on return every
+// lane holds the winning pair.  Doubles are mapped to 64-bit keys that order like the values, and the maximum is taken
+// with three REDUX instructions (high word, low word among the high-word winners, smallest j among the winners) instead
+// of five shuffle rounds of (2 SHFL + SHFL + 2 DSETP + 3 SEL): 50 -> 17 instructions on the hottest loop of the kernel.
 __device__ __forceinline__ void warp_argmax(double& u, int& j) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        double ou = __shfl_xor_sync(FULLW, u, s);
-        int oj = __shfl_xor_sync(FULLW, j, s);
-        if (ou > u || (ou == u && oj < j)) { u = ou; j = oj; }
-    }
+    const long long b = __double_as_longlong(__dadd_rn(u, 0.0));  // -0.0 -> +0.0: equal values, equal keys
+    u32 hi = (u32)((unsigned long long)b >> 32), lo = (u32)b;
+    const u32 neg = (u32)((int)hi >> 31);
+    hi ^= neg | 0x80000000u;
+    lo ^= neg;
+    const u32 mh = __reduce_max_sync(FULLW, hi);
+    const bool top = hi == mh;
+    const u32 ml = __reduce_max_sync(FULLW, top ? lo : 0u);
+    j = __reduce_min_sync(FULLW, (top && lo == ml) ? j : 0x7fffffff);
+    const u32 back = (mh & 0x80000000u) ? 0u : 0xffffffffu;  // undo the key transform
+    u = __longlong_as_double((long long)(((unsigned long long)((mh ^ 0x80000000u) ^ (back & 0x7fffffffu)) << 32) | (ml ^ back)));
+}
+
+// k-th (0-based) set bit of x by the whole (converged) warp: lane l ranks bits l and l+32.  Constant time, where the
+// scalar loop (kth_set_bit) costs 4 instructions per skipped bit.
+__device__ __forceinline__ int warp_kth_set_bit(u64 x, int k, int lane) {
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    const u32 below = (1u << lane) - 1u;
+    const bool a = ((lo >> lane) & 1u) && __popc(lo & below) == k;
+    const bool b = ((hi >> lane) & 1u) && __popc(lo) + __popc(hi & below) == k;
+    const unsigned ba = __ballot_sync(FULLW, a), bb = __ballot_sync(FULLW, b);
+    return ba ? __ffs(ba) - 1 : 31 + __ffs(bb);
+}
+
+// Global loads the compiler keeps where they are written (see the descent loop).
+__device__ __forceinline__ int ld_i32(const int* p) {
+    int v;
+    asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// PUCT score of one edge (MCTS/__init__.py:168-170): Q + (c*P) * (sqrt(Ns) / (1 + N)) in float64, every operation rounded
+// separately.  `nraw` = visits | in-flight << 24; an in-flight visit of a virtual-loss wave is scored as a loss.
+__device__ __forceinline__ double ucb_value(int nraw, double q, double pj, double sq_ns, double c) {
+    const int nj = nraw & N_MASK, vn = (int)((unsigned)nraw >> 24);
+    if (vn) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nj, q), -(double)vn), (double)(nj + vn));
+    const double bound = __ddiv_rn(sq_ns, (double)(1 + nj + vn));
+    return __dadd_rn(q, __dmul_rn(__dmul_rn(c, pj), bound));
+}
+__device__ __noinline__ double ucb_value_call(int nraw, double q, double pj, double sq_ns, double c) {
+    return ucb_value(nraw, q, pj, sq_ns, c);
 }
 
 // The engine step.  Every warp: (1) finishes the simulations that were waiting for their leaves, (2) keeps simulating
@@ -357,8 +407,9 @@ __device__ __forceinline__ void warp_argmax(double& u, int& j) {
 // shared backup site.  Every heavy piece of code - expansion, backup, transposition lookup, move application - exists
 // once in the kernel (round 1 had 3 inlined copies of the expansion, 5 of the backup, 3 of the lookup, 2 of play_move:
 // 10.3 K SASS instructions, the instruction fetch was the top stall reason).
-// 8 CTAs (32 warps) per SM: capped at 64 registers so that all 4096 games of configs[2] are resident at once.
-__global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzTreeParams P) {
+// 7 CTAs (28 warps) per SM = 72 registers: 148 x 28 = 4144 warps, so all 4096 games of configs[2] are still resident at
+// once; at 8 CTAs / 64 registers the descent loop spilled and re-derived the arena pointer on every level.
+__global__ void __launch_bounds__(TREE_WARPS * 32, 7) tree_step_kernel(const OzTreeParams P) {
     __shared__ double s_a[TREE_WARPS][64];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -369,15 +420,21 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
     // self-play ping-pongs two leaf counters: this launch fills P.leaf_count and clears the one the NEXT launch fills
     // (nobody reads it any more: the forward that consumed it ran before this launch) - no memset between steps
     if (P.leaf_count_next && blockIdx.x == 0 && threadIdx.x == 0) *P.leaf_count_next = 0;
-    int status = P.status[slot];
+    // the slot's state leaves in ONE round of loads (a launch typically runs one simulation per game, so the prologue's
+    // dependent round trips are paid per simulation): everything is read before the status is looked at
+    int status = ld_i32(P.status + slot);
+    int sims_left = ld_i32(P.sims_left + slot);
+    int gi = ld_i32(P.slot_game + slot);  // game index: where this episode's records go
+    const int npend_raw = ld_i32(P.pend_count + slot);
+    u64 black = ld_u64(P.black + slot), white = ld_u64(P.white + slot);
+    int player = ld_i32(P.player + slot);
+    int ply = ld_i32(P.ply + slot);
     if (status != OZ_GAME_ACTIVE && status != OZ_GAME_WAIT_LEAF) return;
     const long long t_start = clock64();
 
     unsigned char* arena = P.arena + (size_t)slot * P.arena_stride;
     u64* table = P.table + ((size_t)slot << P.table_log2);
     const int n = P.n;
-    int sims_left = P.sims_left[slot];
-    int gi = P.slot_game[slot];  // game index: where this episode's records go
     u64 c_sims = 0, c_nodes = 0, c_term = 0, c_trans = 0, c_moves = 0, c_hits = 0, c_alias = 0;
     int c_depth = 0;
     SimPath path{0, 0, 0, 0};
@@ -386,14 +443,11 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
     const int V = P.vl_width;
     const bool vl = V > 1;
     // leaves parked by the previous launch, evaluated since: expanded first, in emission order (MCTS/__init__.py:44-57,67-71)
-    const int npend = (status == OZ_GAME_WAIT_LEAF) ? P.pend_count[slot] : 0;
+    const int npend = (status == OZ_GAME_WAIT_LEAF) ? npend_raw : 0;
     int next_pend = 0;
     status = OZ_GAME_ACTIVE;
     int inflight = 0;  // leaves parked by this launch (the current wave)
 
-    u64 black = P.black[slot], white = P.white[slot];
-    int player = P.player[slot];
-    int ply = P.ply[slot];
 
     // the leaf at hand: expanded by the next loop iteration.  src: 0 none, 1 priors in a global row, 2 closed-form hash priors
     int exp_src = 0;
@@ -479,11 +533,11 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
                     const unsigned t1 = __ballot_sync(FULLW, lane + 32 < k && (double)(Np[lane + 32] & N_MASK) == best);
                     const u64 ties = (u64)t0 | ((u64)t1 << 32);
                     const int nt = popc(ties);
-                    if (nt > 1) aj = kth_set_bit(ties, (int)pick_index(episode_draw(base, ply, DRAW_TIE_BREAK), (u32)nt));
+                    if (nt > 1) aj = warp_kth_set_bit(ties, (int)pick_index(episode_draw(base, ply, DRAW_TIE_BREAK), (u32)nt), lane);
                 }
                 const double coin = (double)(episode_draw(base, ply, DRAW_COIN) >> 11) * (1.0 / 9007199254740992.0);
                 if (!(coin <= P.e_greedy)) aj = (int)pick_index(episode_draw(base, ply, DRAW_RANDOM_ACTION), (u32)k);
-                const int sq = kth_set_bit(legal, aj);
+                const int sq = warp_kth_set_bit(legal, aj, lane);
                 if (ply < 64) {
                     size_t ri = (size_t)gi * 64 + ply;
                     if (lane == 0) {
@@ -574,23 +628,25 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
                 const double* Qp = node_Q(h, k);
                 int* Np = node_N(h, k);
                 int* Cp = node_child(h, k);
-                // ONE round of loads per level: header counters + this lane's P/Q/N/child (addresses need only the reference)
-                const int2 cnts = *reinterpret_cast<const int2*>(&h->ns);  // {ns, k}
-                const int vns = h->vns;
-                int c0 = OZ_CH_UNKNOWN, c1 = OZ_CH_UNKNOWN;
+                // ONE round of loads per level: the header counters AND this lane's P/Q/N/child words (their addresses need
+                // only the reference) are issued before anything is computed from them.  Round 1 read "ns" first and took its
+                // square root before touching the rows - two dependent memory round trips per level.
+                // (lanes beyond k re-read slot 0 - k >= 1 - so that the loads are unconditional and leave together.)
+                // The loads are `asm volatile` so that the compiler neither sinks them into the branch that consumes them nor
+                // starts the square root (which needs ns) ahead of them.
+                const int jl = lane < k ? lane : 0;
+                const int nraw0 = ld_i32(Np + jl);
+                int c0 = ld_i32(Cp + jl), c1 = OZ_CH_UNKNOWN;
+                const double q0 = ld_f64(Qp + jl), p0 = ld_f64(Pp + jl);
+                const int ns = ld_i32(&h->ns);
+                const int vns = ld_i32(&h->vns);
+                const double sq_ns = __dsqrt_rn((double)(ns + vns));
                 double bu = -1.0e300; int bj = 1 << 20;
-                const double sq_ns = __dsqrt_rn((double)(cnts.x + vns));
-                for (int j = lane; j < k; j += 32) {
-                    const int nraw = Np[j];
-                    const int cj = Cp[j];
-                    double q = Qp[j];
-                    const double pj = Pp[j];
-                    if (j < 32) c0 = cj; else c1 = cj;
-                    const int nj = nraw & N_MASK, vn = (int)((unsigned)nraw >> 24);
-                    if (vn) q = __ddiv_rn(__dadd_rn(__dmul_rn((double)nj, q), -(double)vn), (double)(nj + vn));  // in-flight = losses
-                    double bound = __ddiv_rn(sq_ns, (double)(1 + nj + vn));
-                    double u = __dadd_rn(q, __dmul_rn(__dmul_rn(P.c, pj), bound));
-                    if (u > bu) { bu = u; bj = j; }
+                if (lane < k) { bu = ucb_value(nraw0, q0, p0, sq_ns, P.c); bj = lane; }
+                if (k > 32 && lane + 32 < k) {  // more than 32 legal moves: a second candidate per lane (rare)
+                    c1 = Cp[lane + 32];
+                    const double u = ucb_value_call(Np[lane + 32], Qp[lane + 32], Pp[lane + 32], sq_ns, P.c);
+                    if (u > bu) { bu = u; bj = lane + 32; }
                 }
                 warp_argmax(bu, bj);
                 path_set(path, lane, depth, (u32)node, (u32)bj);
@@ -609,7 +665,7 @@ __global__ void __launch_bounds__(TREE_WARPS * 32, 8) tree_step_kernel(const OzT
                 }
                 // frontier: get_next_state (othelo_mcts.py:43-49)
                 u64 own = h->own, opp = h->opp;
-                const int sq = kth_set_bit(h->legal, bj);
+                const int sq = warp_kth_set_bit(h->legal, bj, lane);
                 u64 nl;
                 const unsigned fl = play_move_dev(1ull << sq, own, opp, P.full, nl);
                 if (fl & MOVE_FINISHED) {

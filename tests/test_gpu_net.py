@@ -108,6 +108,28 @@ def test_conv2_table_vs_gemm_agree(monkeypatch):
     assert np.abs(outs[0][0] - outs[1][0]).max() <= TOL and np.abs(outs[0][1] - outs[1][1]).max() <= TOL
 
 
+def test_fused_tail_matches_split_launches(monkeypatch):
+    """fc2 + heads as ONE kernel (opt-in OZ_NET_TAIL=fused, oz_tail_kernel: f2 stays in shared memory as the heads' A operand)
+    against the default two generic launches: the accumulation orders are the same, so logits, probabilities, value and the f2 layer
+    must be BIT-identical - including batches that leave the last 128-row tile ragged and batches with more tiles than SMs
+    (a CTA then walks several tiles and every barrier of the kernel changes phase)."""
+    from othellozero_b200 import engine, net
+    for n, C, B, seed in ((8, 512, 301, 31), (6, 128, 148 * 128 + 200, 32), (8, 128, 1, 33)):
+        blob = net.init_weights(n, C, seed=seed, randomize_bn=True)
+        own, opp = _positions(n, min(B, 600), seed)
+        own, opp = np.resize(own, B), np.resize(opp, B)
+        outs = []
+        for mode in ("split", "fused"):
+            monkeypatch.setenv("OZ_NET_TAIL", mode)
+            e = engine.Engine(n, max_games=B + 5, nodes_per_game=2, prior_mode=engine.PRIOR_NET)
+            e.load_weights(blob, C)
+            pi, lg, v = e.net_forward(own, opp)
+            outs.append((pi, lg, v, e.activation(5, B, 1, 512)))
+            e.close()
+        for a, b, name in zip(outs[0], outs[1], ("pi", "logits", "v", "f2")):
+            assert np.array_equal(a, b), f"{name} differs between the fused and the split tail (n={n}, C={C}, B={B})"
+
+
 def test_conv3_wino_vs_direct_agree(monkeypatch):
     """conv3 as 1-D Winograd F(2,3) (transformed bf16 inputs/filters, fp32 accumulate) against the direct implicit GEMM:
     same layer output up to bf16 rounding of the transforms, same logits/value within the north-star tolerance."""
