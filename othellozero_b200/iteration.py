@@ -1,13 +1,13 @@
 """One full training iteration on the whole node (BASELINE.json configs[4]; reference: main.py:71-148):
 
     self-play sharded by game  ->  C2 gather of packed example records  ->  replay buffer (main.py:21-53,87-99)
-    ->  training step sharded over the GPUs (Net/NNet.py:53-68: `epochs` x batch 32, train.train_blob(ddp=True))
+    ->  training step (Net/NNet.py:53-68: `epochs` x batch 32; train.train_blob(ddp="auto"): sharded over the GPUs when the
+        batch is large enough to be worth it, otherwise one GPU replays a CUDA graph of the step and broadcasts the result)
     ->  every rank folds the new weights onto its device tower  ->  arena new vs old, games sharded (main.py:103-148)
 
-One process per GPU (torch.distributed over NCCL); the only collectives are C2 (example gather, once), the gradient /
-BatchNormalization-statistics all-reduces inside the training step, and one all-reduce of the arena's win count.  After
-a DDP training step every rank already holds the new weights, so C1 (weight broadcast, dist.broadcast_weights) is only
-needed for the initial weights.
+One process per GPU (torch.distributed over NCCL); the only collectives are C2 (example gather, once), the training step's
+(gradient / BatchNormalization-statistics all-reduces when it is sharded, else one broadcast of the new weights = C1), and
+one all-reduce of the arena's win count.  train_blob returns the same weights on every rank either way.
 
     python -m othellozero_b200.iteration                       # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 -m othellozero_b200.iteration
@@ -132,7 +132,7 @@ class Trainer:
         arrays = training_arrays(self.buffer.positions(), n)
         new_blob, hist = train.train_blob(self.blob, arrays, n, C, epochs=cfg.epochs, batch_size=cfg.batch_size, lr=cfg.lr,
                                           dropout=cfg.dropout, device=dev if torch.cuda.is_available() else "cpu",
-                                          seed=cfg.seed + self.iteration, ddp=self.world > 1)
+                                          seed=cfg.seed + self.iteration, ddp="auto" if self.world > 1 else False)
         timed("train_s", t0)
         # ---- arena: new vs old, half the games with each colour (main.py:103-131), games sharded over the ranks -------
         t0 = time.perf_counter()

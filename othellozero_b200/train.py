@@ -15,7 +15,8 @@ Two details of what Keras actually computes, reproduced here (both were deviatio
     one for running_var): KerasBatchNorm below.
 Multi-GPU: `train_blob(..., ddp=True)` under torch.distributed shards every global batch over the ranks (rank r takes
 samples r::world), synchronises the BatchNormalization batch statistics and averages the gradients, so N GPUs take the
-SAME optimisation steps one GPU would (tests/test_train_cpu.py, gloo world 2)."""
+SAME optimisation steps one GPU would (tests/test_train_cpu.py, gloo world 2).  `ddp="auto"` shards only batches large
+enough to be worth it; at the reference's batch 32 one GPU replays a CUDA graph of the step instead (see train_blob)."""
 from __future__ import annotations
 
 import numpy as np
@@ -159,18 +160,43 @@ def policy_loss_per_sample(logits, target, n: int, kind: str = "reference"):
     return -(target.view(-1, n, n) * rows.log()).sum(dim=2).mean(dim=1)
 
 
+MIN_SAMPLES_PER_RANK = 32   # ddp="auto": shard a batch over the ranks only if every rank still gets this many samples
+
+
 def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int = 10, batch_size: int = 32,
                lr: float = 1e-3, dropout: float = 0.3, clipvalue: float = 0.5, device=None, seed: int = 0,
-               verbose: bool = False, policy_loss: str = "reference", ddp: bool = False):
+               verbose: bool = False, policy_loss: str = "reference", ddp=False, cuda_graph: bool | None = None):
     """model.fit of Net/NNet.py:67-68.  Returns (new_blob, history) with history = per-epoch mean (loss, pi_loss, v_loss).
     `examples`: the reference's list of (board, policy, z), or a tuple of arrays (boards (E,N,N,2), policies (E,N*N), z (E,)).
+
     ddp=True (inside an initialised torch.distributed group): every rank holds the same examples and the same weights;
     each global batch of `batch_size` is split over the ranks, BatchNormalization statistics and gradients are pooled,
-    and every rank returns the same new blob."""
+    and every rank returns the same new blob.
+    ddp="auto": shard only when that leaves >= MIN_SAMPLES_PER_RANK samples per rank.  At the reference's batch size of 32
+    a step is latency-, not throughput-bound, and sharding it 8 ways costs 8.7 ms per step on 8 B200s (measured: 24 000
+    steps = 208 s) against ~1 ms for one GPU replaying the captured step; so rank 0 trains alone and the result is
+    broadcast (C1) - every rank still returns the same blob.
+    cuda_graph (default: on CUDA without sharding): the optimisation step (gather of the batch, forward, loss, backward,
+    clipping, Adam) is captured once in a CUDA graph and replayed - same arithmetic, one launch per step."""
     import torch.distributed as dist
-    world = _dist_world() if ddp else 1
+    group = _dist_world()
+    shard = bool(ddp) and group > 1 and (ddp != "auto" or batch_size // group >= MIN_SAMPLES_PER_RANK)
+    world = group if shard else 1
     rank = dist.get_rank() if world > 1 else 0
     device = device or ("cuda" if torch.cuda.is_available() else "cpu")
+    on_cuda = str(device).startswith("cuda")
+    if ddp == "auto" and group > 1 and not shard:
+        # rank 0 takes the steps (below, unsharded); the others receive the result
+        new_blob, history = None, None
+        if dist.get_rank() == 0:
+            new_blob, history = train_blob(blob, examples, board_size, channels, epochs, batch_size, lr, dropout, clipvalue,
+                                           device, seed, verbose, policy_loss, ddp=False, cuda_graph=cuda_graph)
+        n_floats = int(np.asarray(blob).size)
+        t = torch.from_numpy(new_blob).to(device) if new_blob is not None else torch.empty(n_floats, dtype=torch.float32, device=device)
+        h = torch.tensor(history if history is not None else [[0.0] * 3] * epochs, dtype=torch.float64, device=device)
+        dist.broadcast(t, src=0)
+        dist.broadcast(h, src=0)
+        return t.cpu().numpy(), [tuple(float(x) for x in row) for row in h.cpu()]
     torch.manual_seed(seed + 7919 * rank)          # dropout masks differ per rank, the weights start equal
     model = OthelloNNTorch(board_size, channels, dropout).load_blob(blob).to(device)
     if world > 1:
@@ -180,42 +206,70 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
     boards, pis, vs = examples if isinstance(examples, tuple) else examples_to_arrays(examples)
     xb, pb, vb = (torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device) for a in (boards, pis, vs))
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=lr, eps=1e-7)  # keras Adam epsilon
     n = xb.shape[0]
+    use_graph = (cuda_graph if cuda_graph is not None else True) and on_cuda and world == 1 and n // batch_size >= 8
+    opt = torch.optim.Adam(params, lr=lr, eps=1e-7, **({"capturable": True, "foreach": True} if use_graph else {}))  # keras Adam epsilon
     gen = torch.Generator(device="cpu").manual_seed(seed)   # the same shuffles on every rank
     history = []
     model.train()
+    tot = torch.zeros(3, dtype=torch.float64, device=device)  # summed on the device: no host sync per step
+
+    def step(gidx):
+        """One optimisation step on the global batch `gidx` (this rank's share of it)."""
+        idx = gidx[rank::world] if world > 1 else gidx
+        logits, v = model(xb.index_select(0, idx))
+        # sums over this rank's samples / the GLOBAL batch size: adding the ranks' gradients gives the batch mean's
+        pi_loss = policy_loss_per_sample(logits, pb.index_select(0, idx), board_size, policy_loss).sum() / gidx.numel()
+        v_loss = ((v - vb.index_select(0, idx)) ** 2).sum() / gidx.numel()
+        loss = pi_loss + v_loss
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        part = torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double()
+        if world > 1:
+            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            dist.all_reduce(part)
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p).clone()
+                off += p.numel()
+        torch.nn.utils.clip_grad_value_(params, clipvalue)      # Adam(clipvalue=0.5)
+        opt.step()
+        tot.add_(part * gidx.numel())
+
+    graph, static_idx, eager_steps = None, None, 0
     for ep in range(epochs):
         perm = torch.randperm(n, generator=gen).to(device)  # keras fit shuffles every epoch
-        tot = torch.zeros(3, dtype=torch.float64, device=device)  # summed on the device: no host sync per step
+        tot.zero_()
         cnt = 0
         for i in range(0, n, batch_size):
             gidx = perm[i:i + batch_size]
             if gidx.numel() < 2:
                 continue  # BatchNorm needs more than one sample
-            idx = gidx[rank::world]
-            logits, v = model(xb[idx])
-            # sums over this rank's samples / the GLOBAL batch size: adding the ranks' gradients gives the batch mean's
-            pi_loss = policy_loss_per_sample(logits, pb[idx], board_size, policy_loss).sum() / gidx.numel()
-            v_loss = ((v - vb[idx]) ** 2).sum() / gidx.numel()
-            loss = pi_loss + v_loss
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            part = torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double()
-            if world > 1:
-                flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
-                dist.all_reduce(flat)
-                dist.all_reduce(part)
-                off = 0
-                for p in params:
-                    p.grad = flat[off:off + p.numel()].view_as(p).clone()
-                    off += p.numel()
-            torch.nn.utils.clip_grad_value_(params, clipvalue)      # Adam(clipvalue=0.5)
-            opt.step()
-            tot += part * gidx.numel()
             cnt += gidx.numel()
+            if not use_graph or gidx.numel() != batch_size:
+                step(gidx)
+                continue
+            if graph is None and eager_steps < 3:
+                # the first full steps run eagerly on a side stream (they are real steps AND the warm-up capture needs)
+                side = torch.cuda.Stream(device=device)
+                side.wait_stream(torch.cuda.current_stream(device))
+                with torch.cuda.stream(side):
+                    step(gidx)
+                torch.cuda.current_stream(device).wait_stream(side)
+                eager_steps += 1
+                continue
+            if graph is None:
+                static_idx = gidx.clone()
+                graph = torch.cuda.CUDAGraph()
+                opt.zero_grad(set_to_none=True)
+                with torch.cuda.graph(graph):   # records only; the replay below is this batch's step
+                    step(static_idx)
+            static_idx.copy_(gidx)
+            graph.replay()
         history.append(tuple(float(x) for x in (tot / max(1, cnt)).cpu()))
         if verbose and rank == 0:
             print(f"epoch {ep + 1}/{epochs}: loss {history[-1][0]:.4f} pi {history[-1][1]:.4f} v {history[-1][2]:.4f}")
+    del graph
     model.eval()
     return model.cpu().to_blob(), history

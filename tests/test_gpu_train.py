@@ -1,0 +1,48 @@
+"""The training step ("next" row) on the device: the CUDA-graph replay of the optimisation step must take
+the same steps as the eager loop (same arithmetic, one launch per step)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _arrays(n, count, seed):
+    rng = np.random.default_rng(seed)
+    boards = (rng.random((count, n, n, 2)) < 0.3).astype(np.float32)
+    boards[..., 1] *= 1.0 - boards[..., 0]
+    pis = np.zeros((count, n * n), dtype=np.float32)
+    pis[np.arange(count), rng.integers(0, n * n, count)] = 1.0
+    return boards, pis, rng.choice([-1.0, 1.0], count).astype(np.float32)
+
+
+def test_cuda_graph_step_equals_eager_step():
+    from othellozero_b200 import net, train
+    n, C = 6, 128
+    blob = net.init_weights(n, C, seed=5)
+    arrays = _arrays(n, 32 * 12 + 5, 6)          # 12 full batches (3 eager warm-up steps, 9 replays) + a ragged one per epoch
+    outs = []
+    for graph in (False, True):
+        new, hist = train.train_blob(blob, arrays, n, C, epochs=2, batch_size=32, dropout=0.0, device="cuda", seed=3,
+                                     cuda_graph=graph)
+        assert np.isfinite(new).all() and np.isfinite(np.array(hist)).all()
+        outs.append((new, np.array(hist)))
+    assert not np.array_equal(outs[0][0], blob)
+    # cuDNN may pick different (equally valid) algorithms under capture: equal up to float32 reassociation
+    assert np.allclose(outs[0][1], outs[1][1], rtol=2e-3, atol=2e-4), (outs[0][1], outs[1][1])
+    scale = np.abs(outs[0][0] - blob).max()
+    assert np.abs(outs[0][0] - outs[1][0]).max() <= 0.05 * scale + 1e-5
+
+
+def test_trained_blob_loads_into_the_device_tower():
+    """B200NNet.train: fit, fold the new weights onto the device tower, predict with them (Net/NNet.py:53-87)."""
+    from othellozero_b200 import net
+    n, C = 6, 128
+    nn_ = net.B200NNet((n, n), C, max_batch=8, blob=net.init_weights(n, C, seed=8))
+    boards, pis, zs = _arrays(n, 32 * 9, 9)
+    board = np.zeros((n, n, 2), dtype=bool)
+    board[2, 3, 0] = board[3, 2, 0] = board[2, 2, 1] = board[3, 3, 1] = True
+    before_pi, before_v = nn_.predict(board)
+    nn_.train(list(zip(boards, pis.reshape(-1, n, n), zs)), epochs=1)
+    after_pi, after_v = nn_.predict(board)
+    assert after_pi.shape == (n, n) and abs(float(after_pi.sum()) - 1.0) < 1e-3
+    assert not np.allclose(before_pi, after_pi)
