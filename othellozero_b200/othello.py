@@ -34,7 +34,7 @@ class OthelloPlayer(Enum):
 
     @property
     def opponent(self):
-        return OthelloPlayer.WHITE if self is OthelloPlayer.BLACK else OthelloPlayer.BLACK
+        return OthelloPlayer(-self.value)
 
 
 _SQUARE_BIT = (np.uint64(1) << (np.arange(8, dtype=np.uint64)[:, None] * np.uint64(8) + np.arange(8, dtype=np.uint64)[None, :]))
@@ -169,11 +169,11 @@ class OthelloGame:
 
     @staticmethod
     def get_board_free_squares(board):
-        return np.argwhere(np.amax(board, axis=2) == 0)
+        return np.argwhere(~np.asarray(board, dtype=bool).any(axis=2))   # row-major, like the reference's argwhere
 
     @staticmethod
     def is_board_square_free(board, row, col):
-        return np.amax(board[row, col]) == 0
+        return np.logical_not(np.asarray(board[row, col], dtype=bool).any())
 
     @staticmethod
     def _own_opp(board, player):
@@ -230,7 +230,9 @@ class OthelloGame:
 
     @staticmethod
     def get_board_winning_player(board):
-        return max(OthelloGame.get_board_players_points(board).items(), key=lambda item: item[1])
+        points = OthelloGame.get_board_players_points(board)
+        top = max(points.values())
+        return next((player, count) for player, count in points.items() if count == top)   # draw -> BLACK (dict order)
 
     @staticmethod
     def get_board_players_points(board):
@@ -250,7 +252,7 @@ class OthelloGame:
 
     @staticmethod
     def invert_board(board):
-        return np.flip(board, axis=2)
+        return board[..., ::-1]   # a view with the two channels swapped
 
     # ---- alpha-zero-general style aliases named in BASELINE.json --------------
     getInitBoard = initial_board
