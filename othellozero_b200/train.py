@@ -214,6 +214,14 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
     model.train()
     tot = torch.zeros(3, dtype=torch.float64, device=device)  # summed on the device: no host sync per step
 
+    flat, flat_views = None, None
+    if world > 1:
+        flat = torch.zeros(sum(p.numel() for p in params) + 3, dtype=torch.float32, device=device)
+        flat_views, off = [], 0
+        for p in params:
+            flat_views.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
     def step(gidx):
         """One optimisation step on the global batch `gidx` (this rank's share of it)."""
         idx = gidx[rank::world] if world > 1 else gidx
@@ -226,13 +234,14 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
         loss.backward()
         part = torch.stack([loss.detach(), pi_loss.detach(), v_loss.detach()]).double()
         if world > 1:
-            flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+            # ONE all-reduce per step: the gradients and the three loss parts travel in a flat buffer whose slices then
+            # serve as the .grad tensors themselves (no per-parameter collectives, no copies back)
+            torch._foreach_copy_(flat_views, [p.grad if p.grad is not None else torch.zeros_like(p) for p in params])
+            flat[-3:] = part.float()
             dist.all_reduce(flat)
-            dist.all_reduce(part)
-            off = 0
-            for p in params:
-                p.grad = flat[off:off + p.numel()].view_as(p).clone()
-                off += p.numel()
+            part = flat[-3:].double()
+            for p, g in zip(params, flat_views):
+                p.grad = g
         torch.nn.utils.clip_grad_value_(params, clipvalue)      # Adam(clipvalue=0.5)
         opt.step()
         tot.add_(part * gidx.numel())

@@ -82,14 +82,14 @@ def test_keras_batchnorm_moves_with_the_biased_variance():
     assert torch.allclose(bn(x), (x - bn.running_mean.view(1, 3, 1, 1)) / torch.sqrt(bn.running_var.view(1, 3, 1, 1) + 1e-3), atol=1e-6)
 
 
-def _ddp_worker(rank, world, port, blob, arrays, q):
+def _ddp_worker(rank, world, port, blob, arrays, q, mode=True):
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch.distributed as dist
     from othellozero_b200 import train as tr
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    new, hist = tr.train_blob(blob, arrays, 6, 128, epochs=2, batch_size=8, dropout=0.0, device="cpu", ddp=True)
+    new, hist = tr.train_blob(blob, arrays, 6, 128, epochs=2, batch_size=8, dropout=0.0, device="cpu", ddp=mode)
     q.put((rank, new, hist))
     dist.destroy_process_group()
 
@@ -122,3 +122,33 @@ def test_ddp_world2_takes_the_same_steps_as_one_process():
     d = np.abs(res[0][1] - single)
     assert np.mean(d < 1e-4) > 0.995 and d.max() <= 6 * 2 * 1e-3 + 1e-4, (np.mean(d < 1e-4), d.max())
     assert np.allclose(np.array(res[0][2]), np.array(h1), atol=2e-4), (res[0][2], h1)
+
+
+def test_ddp_auto_leaves_small_batches_on_one_rank():
+    """ddp="auto": a batch of 8 over 2 ranks is below MIN_SAMPLES_PER_RANK, so rank 0 takes the (unsharded) steps and the
+    result is broadcast - both ranks return exactly the single-process blob and history."""
+    import os
+    import torch.multiprocessing as mp
+    n, C = 6, 128
+    torch.set_num_threads(2)
+    blob = net.init_weights(n, C, seed=6)
+    x = _boards(n, 24, 5)
+    rng = np.random.default_rng(3)
+    pol = np.zeros((24, n * n), dtype=np.float32); pol[np.arange(24), rng.integers(n * n, size=24)] = 1
+    z = rng.choice([-1.0, 1.0], size=24).astype(np.float32)
+    arrays = (x, pol, z)
+    assert 8 // 2 < train.MIN_SAMPLES_PER_RANK
+    torch.set_num_threads(1)
+    single, h1 = train.train_blob(blob, arrays, n, C, epochs=2, batch_size=8, dropout=0.0, device="cpu")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 1000
+    ps = [ctx.Process(target=_ddp_worker, args=(r, 2, port, blob, arrays, q, "auto")) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in ps), key=lambda r: r[0])
+    for p in ps:
+        p.join(timeout=60)
+    for rank, new, hist in res:
+        assert np.array_equal(new, single), rank
+        assert np.allclose(np.array(hist), np.array(h1), atol=1e-12)
