@@ -41,9 +41,9 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
-def ncu_traffic(kernel_substr, fname="r1_ncu_gemm_raw.csv", algorithmic=2 * 4096 * 64 * 512 * 2):
+def ncu_traffic(kernel_substr, fname="r1_ncu_gemm_raw.csv", algorithmic=2 * 4096 * 64 * 512 * 2, boards=4096):
     """dram__bytes_read.sum + dram__bytes_write.sum of the first matching launch in the committed ncu --set full
-    capture (profiles/<fname>; captured at 4096 boards per launch)."""
+    capture (profiles/<fname>; `boards` = boards per launch of that capture)."""
     import csv
     p = os.path.join(ROOT, "profiles", fname)
     try:
@@ -54,7 +54,7 @@ def ncu_traffic(kernel_substr, fname="r1_ncu_gemm_raw.csv", algorithmic=2 * 4096
         for r in rows[2:]:
             if kernel_substr in r[ik]:
                 return {"bytes_per_launch": float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]],
-                        "at_boards_per_launch": 4096, "algorithmic_bytes": algorithmic,
+                        "at_boards_per_launch": boards, "algorithmic_bytes": algorithmic,
                         "source": "profiles/" + fname}
     except Exception:
         pass
@@ -299,7 +299,8 @@ def tensor_roofline(cx, leg, C, conv2, conv3, peaks):
     if table:
         # conv1+conv2 are table reads, not tensor work: the dominant kernel is the conv3 implicit GEMM
         k_ms, k_flop, k_name = float(lt[2]), FLOP_CONV3_PER_BOARD_8, "oz_gemm2_kernel (conv3 implicit GEMM, SM pair, split M tiles)"
-        traffic = ncu_traffic("oz_gemm2_kernel", "r1_ncu_final_raw.csv", 4096 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2)
+        # profiles/r2_ncu_step_raw.csv: one engine step of the steady-state mix, ~3 710 boards per launch
+        traffic = ncu_traffic("oz_gemm2_kernel", "r2_ncu_step_raw.csv", 3710 * (64 + 36) * 512 * 2 + 9 * 512 * 512 * 2, boards=3710)
         tensor_flop_per_eval = FLOP_PER_EVAL_8 - FLOP_CONV1_PER_BOARD_8 - FLOP_CONV2_PER_BOARD_8
         if conv3 == "wino":
             # F(2,3) along y: 4 GEMMs with K = 3C instead of one with 9C -> 2/3 of the direct form's MACs are EXECUTED
@@ -333,10 +334,11 @@ def tensor_roofline(cx, leg, C, conv2, conv3, peaks):
                   "achieved": gb, "peak": l2["read_gbs"], "unit": "GB/s", "frac": gb / l2["read_gbs"],
                   "peak_source": "measured in this run: " + l2["what"],
                   "avg_launch_ms": float(lt[1]),
-                  "traffic": ncu_traffic("conv2_table_gather", "r1_ncu_final_raw.csv", 4096 * GATHER_BYTES_PER_BOARD_8),
-                  "note": "achieved = ALGORITHMIC row bytes (548 KB per board) / launch time; the rows are served by L1 (ncu: 57 % "
-                          "of the sectors) and L2 (DRAM reads are ~4 % of the algorithmic bytes), so the binding unit is the "
-                          "L2->SM path, not HBM; a frac near or above 1 means L1 hits carry part of the traffic"}
+                  "traffic": ncu_traffic("conv2_table_gather", "r2_ncu_step_raw.csv", 3710 * GATHER_BYTES_PER_BOARD_8, boards=3710),
+                  "note": "achieved = ALGORITHMIC row bytes (548 KB per board) / launch time; the rows are served by L1 (ncu: 25 % "
+                          "of the sectors in the steady-state mix) and L2 (49.5 M sectors = 1.58 GB per launch in 134 us = 11.8 TB/s "
+                          "= the probe's peak; DRAM reads are 0.33 GB), so the binding unit is the L2->SM path, not HBM; a frac "
+                          "above 1 means L1 hits carry part of the algorithmic traffic"}
     return roof, gather
 
 
@@ -524,8 +526,8 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-TREE_WARP_INSTR_PER_SIM = 2170       # counted by ncu on tree_step_kernel in the hash-prior mode (profiles/r2_ncu_treeonly_raw.csv):
-                                     # 2.84e10 warp instructions / 1.31e7 simulations of one batch of 4096 whole games
+TREE_WARP_INSTR_PER_SIM = 2020       # counted by ncu on tree_step_kernel in the hash-prior mode (profiles/r2_ncu_treeonly_raw.csv):
+                                     # 2.656e10 warp instructions / 1.313e7 simulations of one batch of 4096 whole games
 
 
 def tree_roofline(sims_per_s_per_gpu, clocks, peaks):
@@ -537,9 +539,9 @@ def tree_roofline(sims_per_s_per_gpu, clocks, peaks):
     return {"bound": "issue", "kernel": "tree_step_kernel", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s",
             "frac": achieved / peak, "traffic": None,
             "hbm_frac": sims_per_s_per_gpu * 1000 / 1e9 / peaks["hbm_gbs"],
-            "note": "achieved = sims/s x 2170 warp instructions per simulation (ncu), peak = 148 SMs x 4 schedulers x sampled SM "
-                    "clock; ncu: issue-active 37 %, stalls per issue: instruction fetch 3.0, fixed-latency 2.4, long scoreboard "
-                    "1.1; hbm_frac = the same throughput against the HBM peak at ~1.0 KB algorithmic bytes per simulation "
+            "note": "achieved = sims/s x 2020 warp instructions per simulation (ncu), peak = 148 SMs x 4 schedulers x sampled SM "
+                    "clock; ncu: stalls per issue: instruction fetch 3.8, fixed-latency 2.3, long scoreboard 1.1 (instruction-cache "
+                    "hit rate 77 %); hbm_frac = the same throughput against the HBM peak at ~1.0 KB algorithmic bytes per simulation "
                     "(SURVEY 8d) - bandwidth is never the limiter"}
 
 

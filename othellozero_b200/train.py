@@ -161,6 +161,7 @@ def policy_loss_per_sample(logits, target, n: int, kind: str = "reference"):
 
 
 MIN_SAMPLES_PER_RANK = 32   # ddp="auto": shard a batch over the ranks only if every rank still gets this many samples
+GRAPH_MIN_BATCHES = 8        # capture the step in a CUDA graph only if an epoch has at least this many full batches
 
 
 def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int = 10, batch_size: int = 32,
@@ -207,7 +208,7 @@ def train_blob(blob, examples, board_size: int, channels: int = 512, epochs: int
     xb, pb, vb = (torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(device) for a in (boards, pis, vs))
     params = [p for p in model.parameters()]
     n = xb.shape[0]
-    use_graph = (cuda_graph if cuda_graph is not None else True) and on_cuda and world == 1 and n // batch_size >= 8
+    use_graph = (cuda_graph if cuda_graph is not None else True) and on_cuda and world == 1 and n // batch_size >= GRAPH_MIN_BATCHES
     opt = torch.optim.Adam(params, lr=lr, eps=1e-7, **({"capturable": True, "foreach": True} if use_graph else {}))  # keras Adam epsilon
     gen = torch.Generator(device="cpu").manual_seed(seed)   # the same shuffles on every rank
     history = []
