@@ -144,6 +144,73 @@ OZ_HD oz_u64 flip_mask(oz_u64 m, oz_u64 own, oz_u64 opp) {
     return f;
 }
 
+// ---- compact forms -------------------------------------------------------------------------------------
+// The same arithmetic with the four axes walked by a loop with run-time shift counts (a 64-bit shift costs two
+// instructions either way): about a quarter of the code.  For callers whose instruction FOOTPRINT matters more than
+// their issue count - the tree kernel, whose hot path has to fit the 32 KB instruction cache; the rules
+// and perft kernels keep the unrolled templates.  tests/test_bitboard_host.py runs both forms over the golden vectors.
+OZ_HD oz_u64 legal_moves_compact(oz_u64 own, oz_u64 opp, oz_u64 full) {
+    const oz_u64 mi = opp & INNER;
+    oz_u64 m = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int a = 0; a < 4; ++a) {
+        const int D = (a == 0) ? 1 : 6 + a;  // 1, 7, 8, 9
+        const oz_u64 mo = (D == 8) ? opp : mi;
+        oz_u64 fl = mo & (own << D), fr = mo & (own >> D);
+        fl |= mo & (fl << D);
+        fr |= mo & (fr >> D);
+        const oz_u64 ml = mo & (mo << D), mr = mo & (mo >> D);
+        fl |= ml & (fl << (2 * D));
+        fr |= mr & (fr >> (2 * D));
+        fl |= ml & (fl << (2 * D));
+        fr |= mr & (fr >> (2 * D));
+        m |= (fl << D) | (fr >> D);
+    }
+    return m & full & ~(own | opp);
+}
+
+OZ_HD oz_u64 flip_mask_compact(oz_u64 m, oz_u64 own, oz_u64 opp) {
+    const oz_u64 all = own | opp;
+    oz_u64 f = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int a = 0; a < 4; ++a) {
+        const int D = (a == 0) ? 1 : 6 + a;  // 1, 7, 8, 9
+        // towards higher bits +1 / +9 must not wrap into column 0 and +7 not into column 7; mirrored going down
+        const oz_u64 wu = (D == 8) ? ~0ull : (D == 7 ? NOT_H : NOT_A);
+        const oz_u64 wd = (D == 8) ? ~0ull : (D == 7 ? NOT_A : NOT_H);
+        {   // flips_up<D>
+            oz_u64 pro = all & wu;
+            oz_u64 gen = (m << D) & wu & opp;
+            gen |= pro & (gen << D);
+            pro &= pro << D;
+            gen |= pro & (gen << (2 * D));
+            pro &= pro << (2 * D);
+            gen |= pro & (gen << (4 * D));
+            const oz_u64 anchors = gen & own;
+            const oz_u64 below = anchors ? (1ull << msb_index(anchors)) - 1ull : 0ull;
+            f |= gen & opp & below;
+        }
+        {   // flips_down<D>
+            oz_u64 pro = all & wd;
+            oz_u64 gen = (m >> D) & wd & opp;
+            gen |= pro & (gen >> D);
+            pro &= pro >> D;
+            gen |= pro & (gen >> (2 * D));
+            pro &= pro >> (2 * D);
+            gen |= pro & (gen >> (4 * D));
+            const oz_u64 anchors = gen & own;
+            const oz_u64 lowest = anchors & (0ull - anchors);
+            const oz_u64 above = anchors ? ~(lowest | (lowest - 1ull)) : 0ull;
+            f |= gen & opp & above;
+        }
+    }
+    return f;
+}
+
 // flip_board_squares, Othello/__init__.py:237-247: mover = own.
 OZ_HD void apply_move(oz_u64 m, oz_u64* own, oz_u64* opp) {
     oz_u64 f = flip_mask(m, *own, *opp);

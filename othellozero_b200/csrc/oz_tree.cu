@@ -62,8 +62,9 @@ __device__ __forceinline__ u64 key_hash(u64 own, u64 opp) {
 // so no caller state is forced into local memory): every call site costs a few instructions instead of a few hundred,
 // which is what keeps the kernel's hot loops inside the instruction cache (round 1: ~10.3 K SASS instructions, fetch
 // stalls on top of the stall list).
-__device__ __noinline__ u64 flip_mask_call(u64 m, u64 own, u64 opp) { return flip_mask(m, own, opp); }
-__device__ __noinline__ u64 legal_moves_call(u64 own, u64 opp, u64 full) { return legal_moves(own, opp, full); }
+// ... and they use the looped compact forms of oz_bitboard.cuh (a quarter of the unrolled templates' code, same issue count).
+__device__ __noinline__ u64 flip_mask_call(u64 m, u64 own, u64 opp) { return flip_mask_compact(m, own, opp); }
+__device__ __noinline__ u64 legal_moves_call(u64 own, u64 opp, u64 full) { return legal_moves_compact(own, opp, full); }
 
 // play_move (oz_bitboard.cuh) over the out-of-line helpers.
 __device__ __forceinline__ unsigned play_move_dev(u64 m, u64& own, u64& opp, u64 full, u64& next_legal) {
@@ -90,6 +91,7 @@ __device__ __noinline__ u64 table_find(const u64* __restrict__ table, int log2ca
     u32 mask = (1u << log2cap) - 1u;
     u32 fp = (u32)(h >> 32);
     u32 start = (u32)h & mask;
+#pragma unroll 1
     for (u32 w = 0; w <= mask; w += 32) {
         u32 idx = (start + w + (u32)lane) & mask;
         u64 ent = table[idx];
@@ -234,17 +236,19 @@ __device__ __forceinline__ int expand_node(const OzTreeParams& P, int slot, int 
         }
     }
     __syncwarp();
-    // np.sum pairwise (8 strided accumulators, then a fixed tree, then the tail)
-    int body = nsq - (nsq % 8);
-    double acc = 0.0;
+    // np.sum pairwise (8 strided accumulators, then a fixed tree, then the tail).  Rolled loops and the eight partial sums
+    // exchanged through shared memory (sa[64..71]) instead of eight 64-bit shuffles: a tenth of the code, same additions.
+    const int body = nsq - (nsq % 8);
     if (lane < 8) {
-        acc = sa[lane];
+        double acc = sa[lane];
+#pragma unroll 1
         for (int i = 8; i < body; i += 8) acc = __dadd_rn(acc, sa[i + lane]);
+        sa[64 + lane] = acc;
     }
-    double r0 = __shfl_sync(FULLW, acc, 0), r1 = __shfl_sync(FULLW, acc, 1), r2 = __shfl_sync(FULLW, acc, 2),
-           r3 = __shfl_sync(FULLW, acc, 3), r4 = __shfl_sync(FULLW, acc, 4), r5 = __shfl_sync(FULLW, acc, 5),
-           r6 = __shfl_sync(FULLW, acc, 6), r7 = __shfl_sync(FULLW, acc, 7);
-    double sum = __dadd_rn(__dadd_rn(__dadd_rn(r0, r1), __dadd_rn(r2, r3)), __dadd_rn(__dadd_rn(r4, r5), __dadd_rn(r6, r7)));
+    __syncwarp();
+    double sum = __dadd_rn(__dadd_rn(__dadd_rn(sa[64], sa[65]), __dadd_rn(sa[66], sa[67])),
+                           __dadd_rn(__dadd_rn(sa[68], sa[69]), __dadd_rn(sa[70], sa[71])));
+#pragma unroll 1
     for (int i = body; i < nsq; ++i) sum = __dadd_rn(sum, sa[i]);
 
     OzNodeHdr* h = node_at(arena, off);
@@ -306,6 +310,7 @@ __device__ __forceinline__ int cache_probe(const OzTreeParams& P, u64 own, u64 o
     const u64 bucket = (h >> 3) & (((u64)1 << P.cache_log2_buckets) - 1ull);
     volatile u64* tags = (volatile u64*)P.cache_tags + bucket * 8;
     *fp_out = fp;
+#pragma unroll 1
     for (int attempt = 0; attempt < 4096; ++attempt) {
         u64 t = (lane < 8) ? tags[lane] : 0ull;
         unsigned match = __ballot_sync(FULLW, lane < 8 && (t >> 2) == fp);
@@ -410,7 +415,7 @@ __device__ __noinline__ double ucb_value_call(int nraw, double q, double pj, dou
 // 7 CTAs (28 warps) per SM = 72 registers: 148 x 28 = 4144 warps, so all 4096 games of configs[2] are still resident at
 // once; at 8 CTAs / 64 registers the descent loop spilled and re-derived the arena pointer on every level.
 __global__ void __launch_bounds__(TREE_WARPS * 32, 7) tree_step_kernel(const OzTreeParams P) {
-    __shared__ double s_a[TREE_WARPS][64];
+    __shared__ double s_a[TREE_WARPS][72];  // [0,64): masked priors of the node being expanded, [64,72): its partial sums
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int slot = blockIdx.x * TREE_WARPS + wib;

@@ -8,6 +8,12 @@ unsigned long long bbh_legal(unsigned long long own, unsigned long long opp, int
 unsigned long long bbh_flip(int sq, unsigned long long own, unsigned long long opp) {
     return ozbb::flip_mask(1ull << sq, own, opp);
 }
+unsigned long long bbh_legal_compact(unsigned long long own, unsigned long long opp, int n) {
+    return ozbb::legal_moves_compact(own, opp, ozbb::full_mask(n));
+}
+unsigned long long bbh_flip_compact(int sq, unsigned long long own, unsigned long long opp) {
+    return ozbb::flip_mask_compact(1ull << sq, own, opp);
+}
 unsigned bbh_play(int sq, unsigned long long* own, unsigned long long* opp, int n, unsigned long long* next_legal) {
     return ozbb::play_move(1ull << sq, own, opp, ozbb::full_mask(n), next_legal);
 }

@@ -21,6 +21,10 @@ def lib():
         L.bbh_legal.restype = u64
         L.bbh_flip.argtypes = [C.c_int, u64, u64]
         L.bbh_flip.restype = u64
+        L.bbh_legal_compact.argtypes = [u64, u64, C.c_int]
+        L.bbh_legal_compact.restype = u64
+        L.bbh_flip_compact.argtypes = [C.c_int, u64, u64]
+        L.bbh_flip_compact.restype = u64
         L.bbh_play.argtypes = [C.c_int, C.POINTER(u64), C.POINTER(u64), C.c_int, C.POINTER(u64)]
         L.bbh_play.restype = C.c_uint
         L.bbh_kth.argtypes = [u64, C.c_int]

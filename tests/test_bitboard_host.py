@@ -12,27 +12,36 @@ def _legal_list(mask):
     return [i for i in range(64) if (mask >> i) & 1]
 
 
+def _forms(L, compact):
+    """(legal, flip) of the unrolled templates or of the looped compact forms the tree kernel uses."""
+    return (L.bbh_legal_compact, L.bbh_flip_compact) if compact else (L.bbh_legal, L.bbh_flip)
+
+
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("n", [4, 6, 8])
-def test_bitboard_vs_golden(golden_rules, n):
+def test_bitboard_vs_golden(golden_rules, n, compact):
     L = bbhost.lib()
+    legal, flip = _forms(L, compact)
     for rec in golden_rules[str(n)]:
         b, w = int(rec["b"], 16), int(rec["w"], 16)
         for ch, (own, opp) in ((0, (b, w)), (1, (w, b))):
             exp = rec[f"moves{ch}"]
-            assert _legal_list(L.bbh_legal(own, opp, n)) == [m[0] for m in exp]
+            assert _legal_list(legal(own, opp, n)) == [m[0] for m in exp]
             for sq, fb, fw in exp:
-                f = L.bbh_flip(sq, own, opp)
+                f = flip(sq, own, opp)
                 no, np_ = own | f | (1 << sq), opp & ~f
                 got = (no, np_) if ch == 0 else (np_, no)
                 assert got == (int(fb, 16), int(fw, 16))
-        fin = (L.bbh_legal(b, w, n) == 0) and (L.bbh_legal(w, b, n) == 0)
+        fin = (legal(b, w, n) == 0) and (legal(w, b, n) == 0)
         assert fin == rec["finished"]
 
 
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("n", [4, 6, 8])
-def test_bitboard_random_positions_vs_oracle(n):
+def test_bitboard_random_positions_vs_oracle(n, compact):
     """Arbitrary (not necessarily reachable) positions stress the flip-through quirk and edges."""
     L = bbhost.lib()
+    legal, flip = _forms(L, compact)
     rng = np.random.default_rng(n)
     for _ in range(1500):
         occ = rng.random((n, n)) < rng.uniform(0.2, 0.95)
@@ -42,10 +51,10 @@ def test_bitboard_random_positions_vs_oracle(n):
         board[..., 1] = occ & ~col
         own, opp = oracle.board_to_bits(board)
         acts = oracle.valid_actions(board, 0)
-        assert _legal_list(L.bbh_legal(own, opp, n)) == [r * 8 + c for r, c in acts]
+        assert _legal_list(legal(own, opp, n)) == [r * 8 + c for r, c in acts]
         for r, c in acts:
             nb = oracle.flip_board(board, 0, r, c)
-            f = L.bbh_flip(r * 8 + c, own, opp)
+            f = flip(r * 8 + c, own, opp)
             assert (own | f | (1 << (r * 8 + c)), opp & ~f) == oracle.board_to_bits(nb)
 
 
