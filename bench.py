@@ -225,6 +225,8 @@ def selfplay_leg(cx, *, games, sims, vl, cache_log2, window, steps, warmup, mode
         # every slot always holds a game: a game lasts <= 60 moves, so 1 + (steps + warmup) // 30 queued generations
         # are more than the timed region can consume
         total = G * (2 + (steps + warmup) // 30)
+        if mode == E.PRIOR_HASH:
+            total = 4 * G   # one tree-only step = 4 generations through the G slots (see tree_batch)
         first_id = cx.next_id + cx.rank * total
         cx.next_id += cx.world * total
         sb, sw, sp = synthetic_starts(E, total, args.seed, first_id, cx.local, spread)
@@ -234,8 +236,11 @@ def selfplay_leg(cx, *, games, sims, vl, cache_log2, window, steps, warmup, mode
         stream = torch.cuda.ExternalStream(eng.stream(), device=f"cuda:{cx.local}")
 
         def tree_batch():
-            # hash priors: a whole game runs inside ONE tree kernel launch, so a step is one complete batch of games
-            eng.selfplay_begin(G, sims, 1.0, 0.9, -1, sb[:G], sw[:G], sp[:G], ids[:G])
+            # hash priors: whole games run inside ONE tree kernel launch, so a step is one complete job: 4 x G games through
+            # the G slots - finished slots take queued games, as in the engine's normal operation; with G games only, the
+            # launch ends with a long tail of a few long games on an otherwise empty GPU (ncu: 16 of 28 warps per SM
+            # resident on average) and the figure measures the tail, not the kernel
+            eng.selfplay_begin(total, sims, 1.0, 0.9, -1, sb, sw, sp, ids)
             eng.selfplay_run(-1)
             return eng.counters()
 
@@ -473,7 +478,7 @@ def run_ours(args):
                                         "slots per step), steady-state mix of game phases (visit counts differ from the sequential reference by "
                                         "design); 512 games x waves of 8 measure 4.4 M sims/s in the same window")
         short("tree_only", games=G, sims=sims, vl=1, cache_log2=0, window="opening", steps=2, warmup=1, mode=E.PRIOR_HASH)
-        extras["tree_only"]["what"] = "rules + tree kernels alone (closed-form priors, no network): complete batches of 4096 games"
+        extras["tree_only"]["what"] = "rules + tree kernels alone (closed-form priors, no network): complete jobs of 4 x 4096 games through 4096 slots"
         try:
             pl = perft_leg(args, E, peaks, rank, world, local, barrier, 5, 3)
             extras["perft"] = {k: pl[k] for k in ("metric", "value", "unit", "ms_per_step", "roofline", "e2e")}
@@ -500,7 +505,7 @@ def run_ours(args):
                    "board": 8, "sims_per_move": sims, "games_per_gpu": G, "channels": C, "e_greedy": 0.9, "temperature": 1,
                    "eval_cache_log2": args.eval_cache_log2, "vl_width": args.vl, "window": window_txt,
                    "step": (f"{leg['spm']} engine steps (tree kernel + leaf-batch net forward) = >=1 move per game"
-                            if mode == E.PRIOR_NET else f"one complete batch of {G} games (a whole game runs inside one launch)"),
+                            if mode == E.PRIOR_NET else f"one complete job of {4 * G} games through {G} slots (whole games run inside one launch; finished slots take queued games)"),
                    "l2": "inputs larger than L2: activations 0.8 GB/forward, node pools %.1f GB" % (G * (sims * 61 + 64) * 432 / 1e9),
                    "games_queued_per_gpu": leg["total_queued"], "parallelism": f"games sharded x{world}"},
         "moves_per_s": leg["moves"] / (ms / 1e3), "games_per_s_est": leg["moves"] / (ms / 1e3) / 60.0,
@@ -527,8 +532,8 @@ def run_ours(args):
     print(json.dumps(out))
 
 
-TREE_WARP_INSTR_PER_SIM = 2020       # counted by ncu on tree_step_kernel in the hash-prior mode (profiles/r2_ncu_treeonly_raw.csv):
-                                     # 2.656e10 warp instructions / 1.313e7 simulations of one batch of 4096 whole games
+TREE_WARP_INSTR_PER_SIM = 2130       # counted by ncu on tree_step_kernel in the hash-prior mode (profiles/r2_ncu_treeonly_raw.csv):
+                                     # 1.119e11 warp instructions / 5.25e7 simulations of one job of 4 x 4096 whole games
 
 
 def tree_roofline(sims_per_s_per_gpu, clocks, peaks):
@@ -540,9 +545,9 @@ def tree_roofline(sims_per_s_per_gpu, clocks, peaks):
     return {"bound": "issue", "kernel": "tree_step_kernel", "achieved": achieved, "peak": peak, "unit": "G warp-instr/s",
             "frac": achieved / peak, "traffic": None,
             "hbm_frac": sims_per_s_per_gpu * 1000 / 1e9 / peaks["hbm_gbs"],
-            "note": "achieved = sims/s x 2020 warp instructions per simulation (ncu), peak = 148 SMs x 4 schedulers x sampled SM "
-                    "clock; ncu: stalls per issue: instruction fetch 3.8, fixed-latency 2.3, long scoreboard 1.1 (instruction-cache "
-                    "hit rate 77 %); hbm_frac = the same throughput against the HBM peak at ~1.0 KB algorithmic bytes per simulation "
+            "note": "achieved = sims/s x 2130 warp instructions per simulation (ncu), peak = 148 SMs x 4 schedulers x sampled SM "
+                    "clock; ncu: issue-active 61 %, stalls per issue: fixed-latency 2.4, instruction fetch 2.2, long scoreboard 1.1 "
+                    "(instruction-cache hit rate 88 %); hbm_frac = the same throughput against the HBM peak at ~1.0 KB algorithmic bytes per simulation "
                     "(SURVEY 8d) - bandwidth is never the limiter"}
 
 
