@@ -127,7 +127,8 @@ int oz_search_set_roots(oz_engine* e, const uint64_t* black, const uint64_t* whi
 /* num_sims x OthelloMCTS.simulate(root) for every game, strictly sequential per game (bit-exact mode).
  * OZ_PRIOR_HASH / OZ_PRIOR_NET run to completion; OZ_PRIOR_HOST returns after each wave of leaves:
  * *n_leaves > 0 means "evaluate them (oz_search_get_leaves / oz_search_put_priors) and call
- * oz_search_continue"; 0 means done. */
+ * oz_search_continue"; 0 means done.  OZ_ERR_NOMEM when a game's node pool / table filled up before its simulations
+ * were done (the reference's dicts grow without bound, MCTS/__init__.py:19-28; here nodes_per_game bounds them). */
 int oz_search_begin(oz_engine* e, int32_t num_sims, int32_t* n_leaves);
 int oz_search_continue(oz_engine* e, int32_t* n_leaves);
 /* Pending leaves in canonical form (the board passed to predict, othelo_mcts.py:82-88). HOST buffers. */

@@ -176,15 +176,15 @@ static int read_leaf_count(oz_engine* e, int* n) {
     return OZ_OK;
 }
 
-__global__ void count_waiting_kernel(const OzTreeParams P, int* out) {
+__global__ void count_status_kernel(const OzTreeParams P, int wanted, int* out) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < P.G && P.status[g] == OZ_GAME_WAIT_LEAF) atomicAdd(out, 1);
+    if (g < P.G && P.status[g] == wanted) atomicAdd(out, 1);
 }
 
-static int count_waiting(oz_engine* e, int* n) {
+static int count_status(oz_engine* e, int wanted, int* n) {
     int* d = e->leaf_count_base + 2;
     OZ_CUDA(cudaMemsetAsync(d, 0, sizeof(int), e->stream));
-    count_waiting_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, d);
+    count_status_kernel<<<(e->tp.G + 255) / 256, 256, 0, e->stream>>>(e->tp, wanted, d);
     OZ_CUDA(cudaGetLastError());
     e->launches++;
     OZ_CUDA(cudaMemcpyAsync(&e->h_pinned[4], d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
@@ -223,12 +223,21 @@ static int search_pump(oz_engine* e, int32_t* n_leaves) {
             e->host_leaves = nl; *n_leaves = nl; return OZ_OK;
         }
         int waiting = 0;
-        if ((rc = count_waiting(e, &waiting))) return rc;
+        if ((rc = count_status(e, OZ_GAME_WAIT_LEAF, &waiting))) return rc;
         if (waiting == 0) { *n_leaves = 0; break; }
         if (nl > 0 && (rc = eval_leaves(e))) return rc;
     }
     OZ_CUDA(cudaStreamSynchronize(e->stream));
     e->host_leaves = 0;
+    // a game whose node pool or table filled up stopped short of num_sims: report it instead of returning thinner counts
+    int full = 0;
+    int rc = count_status(e, OZ_GAME_POOL_FULL, &full);
+    if (rc) return rc;
+    if (full > 0) {
+        oz_set_error("node pool exhausted in %d game(s) before the requested simulations were done (nodes_per_game = %d "
+                     "is sized for 16 children per node on average)", full, e->cfg.nodes_per_game);
+        return OZ_ERR_NOMEM;
+    }
     return OZ_OK;
 }
 

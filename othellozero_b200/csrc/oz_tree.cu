@@ -414,7 +414,10 @@ __device__ __noinline__ double ucb_value_call(int nraw, double q, double pj, dou
 // 10.3 K SASS instructions, the instruction fetch was the top stall reason).
 // 7 CTAs (28 warps) per SM = 72 registers: 148 x 28 = 4144 warps, so all 4096 games of configs[2] are still resident at
 // once; at 8 CTAs / 64 registers the descent loop spilled and re-derived the arena pointer on every level.
-__global__ void __launch_bounds__(TREE_WARPS * 32, 7) tree_step_kernel(const OzTreeParams P) {
+#ifndef OZ_TREE_MIN_CTAS
+#define OZ_TREE_MIN_CTAS 7
+#endif
+__global__ void __launch_bounds__(TREE_WARPS * 32, OZ_TREE_MIN_CTAS) tree_step_kernel(const OzTreeParams P) {
     __shared__ double s_a[TREE_WARPS][72];  // [0,64): masked priors of the node being expanded, [64,72): its partial sums
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;

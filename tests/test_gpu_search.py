@@ -148,6 +148,15 @@ def test_pool_exhaustion_is_reported(E):
     e.close()
 
 
+def test_pool_exhaustion_is_reported_by_the_search_api(E):
+    """oz_search_begin must not return thinner visit counts silently when a game's node pool fills up."""
+    e = E.Engine(8, 2, 16, E.PRIOR_HASH)
+    e.reset(2)
+    with pytest.raises(MemoryError):
+        e.search(400)
+    e.close()
+
+
 def test_selfplay_full_size_properties(E):
     """BASELINE configs[2] size (4096 games x 100 sims/move, 8x8) with the closed-form priors: size-independent
     invariants for every game + oracle comparison for a sample."""
@@ -349,3 +358,34 @@ def test_seed_and_game_id_do_not_commute(E):
     assert len(set(a.values()) & set(b.values())) <= 1
     c = play(0, list(range(G)))
     assert a == c                                              # same (seed, ids) -> same games
+
+
+def test_roots_with_more_than_32_legal_moves(E):
+    """Artificial (unreachable) positions with 33-35 legal moves: a lane then scores two children per level (the rare
+    second-candidate path of the descent) and the chosen square comes from the high half of the k-th-set-bit ballot.
+    Root visit counts, Ns, node counts and Q values/types must equal the oracle's."""
+    n, sims = 8, 300
+    roots = [(0x40202c04468c2000, 0x5e400a10624c00), (0x8e42000678420, 0x76125202087200),
+             (0x1108282441460180, 0x5446503220e600)]
+    for own, opp in roots:
+        board = oracle.bits_to_board(own, opp, n)                 # own = BLACK, BLACK to move
+        k = len(oracle.valid_actions(board, 0))
+        assert k > 32
+        e = E.Engine(n, 1, 4 * sims, E.PRIOR_HASH)                 # pools are sized for 16 children per node: these nodes have 30+
+        e.reset(1, [own], [opp], [0])
+        e.search(sims)
+        v, ns = e.visits()
+        q, p, tag = e.root_stats(0)
+        m = oracle.Mcts(n)
+        for _ in range(sims):
+            m.simulate(board, 0)
+        rns, rv = m.visits(board)
+        assert int(ns[0]) == rns and visits_to_grid(v[0], n).tolist() == rv.reshape(-1).tolist(), hex(own)
+        assert e.counters()["nodes"] == m.nodes
+        rq, rp, rtag = m.node_stats(board)
+        for r in range(n):
+            for c in range(n):
+                if rtag[r, c] >= 0:
+                    assert q[r * 8 + c] == rq[r, c] and p[r * 8 + c] == rp[r, c] and tag[r * 8 + c] == rtag[r, c]
+        assert int((rv > 0).sum()) >= 33 - 1                      # the search really spreads over > 32 children
+        e.close()
