@@ -90,12 +90,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Bounded wait: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU.  The bound is wall time
+// (%globaltimer, looked at every 256 failed attempts), not a spin count: one try_wait may itself block for a
+// hardware-defined time, and a count of 2^27 of those turned a mis-sized TMA transaction into a hang of minutes.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+    unsigned long long t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 27)) __trap();
+        if ((++spins & 255u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ull) __trap();  // 4 s: no kernel of the tower runs for more than a few ms
+        }
     }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
