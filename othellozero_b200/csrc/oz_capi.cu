@@ -196,7 +196,8 @@ static int count_status(oz_engine* e, int wanted, int* n) {
 // Evaluate the pending leaf batch with the device network (count stays on the device).
 static int eval_leaves_net(oz_engine* e) {
     // the heads kernel's epilogue publishes the new evaluation-cache entries (no separate cache_publish launch)
-    return oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, e->leaf_logits,
+    // (no logits: the search consumes probabilities and the value only)
+    return oz_net_forward(e, e->tp.leaf_own, e->tp.leaf_opp, e->tp.leaf_count, e->n_games * e->tp.vl_width, e->leaf_pi, nullptr,
                           e->leaf_v, e->tp.cache_tags != nullptr);
 }
 

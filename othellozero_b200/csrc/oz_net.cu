@@ -421,12 +421,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 64; ++j) { ex[j] = (j < nsq) ? expf(lg[j] - mx) : 0.f; sum += ex[j]; }
                     const float inv = 1.0f / sum;
-                    float* lrow = p.logits + grow * 64;
                     float* prow = p.pi + grow * 64;
 #pragma unroll
-                    for (int j = 0; j < 64; j += 4) {
-                        *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
+                    for (int j = 0; j < 64; j += 4)
                         *reinterpret_cast<float4*>(prow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                    if (p.logits) {  // only the parity / inspection entry points ask for the logits; self-play steps do not
+                        float* lrow = p.logits + grow * 64;
+#pragma unroll
+                        for (int j = 0; j < 64; j += 4)
+                            *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
                     }
                     const float val = tanhf(nsq == 64 ? lg[64] : lg[36]);
                     p.v[grow] = val;
@@ -952,12 +955,15 @@ oz_tail_kernel(const __grid_constant__ CUtensorMap mapA /* f1: (1024, 1, 1, B), 
 #pragma unroll
                 for (int j = 0; j < 64; ++j) { ex[j] = (j < nsq) ? expf(lg[j] - mx) : 0.f; sum += ex[j]; }
                 const float inv = 1.0f / sum;
-                float* lrow = p.logits + grow * 64;
                 float* prow = p.pi + grow * 64;
 #pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
+                for (int j = 0; j < 64; j += 4)
                     *reinterpret_cast<float4*>(prow + j) = make_float4(ex[j] * inv, ex[j + 1] * inv, ex[j + 2] * inv, ex[j + 3] * inv);
+                if (p.logits) {
+                    float* lrow = p.logits + grow * 64;
+#pragma unroll
+                    for (int j = 0; j < 64; j += 4)
+                        *reinterpret_cast<float4*>(lrow + j) = make_float4(lg[j], lg[j + 1], lg[j + 2], lg[j + 3]);
                 }
                 const float val = tanhf(nsq == 64 ? lg[64] : lg[36]);
                 p.v[grow] = val;
