@@ -455,13 +455,15 @@ def run_ours(args):
     # ---- extras (N = 1): the other configurations the driver should witness, each a short leg with its own roofline ----
     extras = {}
     if world == 1 and not args.no_extras and not tree_only and args.vl <= 1:
-        def short(name, **kw):
+        def short(name, conv3=None, **kw):
+            conv3 = conv3 or args.conv3
             try:
+                os.environ["OZ_NET_CONV3"] = conv3      # read when the leg's engine is created
                 lg = selfplay_leg(cx, **kw)
                 r = {"value": lg["sims"] / (lg["ms"] / 1e3), "unit": "sims/s", "steps": lg["steps"], "ms_per_step": lg["ms"] / lg["steps"],
                      "evals_per_sim": lg["evals"] / max(1.0, lg["sims"]), "net_evals_per_s": lg["evals"] / (lg["ms"] / 1e3)}
                 if kw["mode"] == E.PRIOR_NET:
-                    roof, _ = tensor_roofline(cx, lg, C, args.conv2, args.conv3, peaks)
+                    roof, _ = tensor_roofline(cx, lg, C, args.conv2, conv3, peaks)
                     r["roofline"] = {k: roof[k] for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "avg_boards_per_launch",
                                                           "avg_launch_ms", "whole_step_tensor_frac", "layer_ms")}
                 else:
@@ -469,10 +471,17 @@ def run_ours(args):
                 extras[name] = r
             except Exception as ex:  # an extra must never cost the headline line
                 extras[name] = {"error": repr(ex)[:300]}
+            finally:
+                os.environ["OZ_NET_CONV3"] = args.conv3 if args.conv2 == "table" else "direct"
         short("opening_window", games=G, sims=sims, vl=1, cache_log2=args.eval_cache_log2, window="opening", steps=5, warmup=3, mode=E.PRIOR_NET)
         extras["opening_window"]["what"] = "round 1's default window: every game within its first ~16 plies, where the evaluation cache shares most"
         short("cache_off", games=G, sims=sims, vl=1, cache_log2=0, window="steady", steps=5, warmup=3, mode=E.PRIOR_NET)
         extras["cache_off"]["what"] = "same workload without the cross-game evaluation cache: one network evaluation per expanded node"
+        if args.conv2 == "table" and args.conv3 == "direct":
+            short("conv3_winograd", conv3="wino", games=G, sims=sims, vl=1, cache_log2=args.eval_cache_log2, window="steady", steps=5, warmup=3,
+                  mode=E.PRIOR_NET)
+            extras["conv3_winograd"]["what"] = ("the headline workload with conv3 as the opt-in 1-D Winograd F(2,3) SM-pair kernel (--conv3 wino; DESIGN 3b): "
+                                               "2/3 of the direct form's tensor FLOPs are executed, so its roofline fraction counts executed FLOPs")
         short("config3_vl4", games=2048, sims=800, vl=4, cache_log2=args.eval_cache_log2, window="steady", steps=3, warmup=3, mode=E.PRIOR_NET)
         extras["config3_vl4"]["what"] = ("BASELINE.json configs[3] on ONE GPU: 800 sims/move, C=512, 2048 games x virtual-loss waves of 4 (8192 leaf "
                                         "slots per step), steady-state mix of game phases (visit counts differ from the sequential reference by "
