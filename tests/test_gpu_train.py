@@ -17,28 +17,32 @@ def _arrays(n, count, seed):
 
 def test_cuda_graph_step_equals_eager_step(monkeypatch):
     """Same start, same batches: [3 eager steps + N replays of the captured step] against [3 + N eager steps].  float32
-    convolutions (no TF32), no dropout, so the two runs differ only by the reassociation inside cuDNN's reductions - which
-    Adam turns into +-lr steps on gradient components that are pure rounding noise (see tests/test_train_cpu.py): the bulk
-    of the parameters must agree tightly, the worst element by a few learning rates, the loss trajectory closely."""
+    convolutions (no TF32), no dropout, so the runs differ only by the reassociation inside cuDNN's reductions (atomics in the
+    weight-gradient and BatchNormalization kernels make even two EAGER runs differ) - which Adam turns into +-lr steps on
+    gradient components that are pure rounding noise (see tests/test_train_cpu.py) and later steps amplify.  So the yardstick
+    is the run-to-run spread of the eager loop itself: the graph run must agree with an eager run as well as a second eager
+    run does, the worst element by a few learning rates, the loss trajectory closely."""
     import torch
     from othellozero_b200 import net, train
     monkeypatch.setattr(train, "GRAPH_MIN_BATCHES", 1)
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     n, C, lr = 6, 128, 1e-3
     blob = net.init_weights(n, C, seed=5)
+    agree = lambda a, b: float(np.mean(np.abs(a - b) < 1e-4))
     for full_batches, ragged in ((4, 0), (7, 5)):
         arrays = _arrays(n, 32 * full_batches + ragged, 6 + full_batches)
         outs = []
-        for graph in (False, True):
+        for graph in (False, False, True):
             new, hist = train.train_blob(blob, arrays, n, C, epochs=1, batch_size=32, lr=lr, dropout=0.0, device="cuda", seed=3,
                                          cuda_graph=graph)
             assert np.isfinite(new).all() and np.isfinite(np.array(hist)).all()
             outs.append((new, np.array(hist)))
         steps = full_batches + (1 if ragged else 0)
         assert not np.array_equal(outs[0][0], blob)
-        d = np.abs(outs[0][0] - outs[1][0])
-        assert np.mean(d < 1e-4) > 0.99 and d.max() <= 2 * lr * steps + 1e-4, (full_batches, np.mean(d < 1e-4), d.max())
-        assert np.allclose(outs[0][1], outs[1][1], rtol=2e-2), (outs[0][1], outs[1][1])
+        noise, got = agree(outs[0][0], outs[1][0]), agree(outs[0][0], outs[2][0])
+        assert got >= 0.9 * noise - 0.02, (full_batches, "eager vs eager", noise, "eager vs graph", got)
+        assert np.abs(outs[0][0] - outs[2][0]).max() <= 2 * lr * steps + 1e-4
+        assert np.allclose(outs[0][1], outs[2][1], rtol=5e-2), (outs[0][1], outs[2][1])
 
 
 def test_trained_blob_loads_into_the_device_tower():
