@@ -16,33 +16,33 @@ def _arrays(n, count, seed):
 
 
 def test_cuda_graph_step_equals_eager_step(monkeypatch):
-    """Same start, same batches: [3 eager steps + N replays of the captured step] against [3 + N eager steps].  float32
-    convolutions (no TF32), no dropout, so the runs differ only by the reassociation inside cuDNN's reductions (atomics in the
-    weight-gradient and BatchNormalization kernels make even two EAGER runs differ) - which Adam turns into +-lr steps on
-    gradient components that are pure rounding noise (see tests/test_train_cpu.py) and later steps amplify.  So the yardstick
-    is the run-to-run spread of the eager loop itself: the graph run must agree with an eager run as well as a second eager
-    run does, the worst element by a few learning rates, the loss trajectory closely."""
+    """Same start, same batches: [3 eager steps + 1 replay of the captured step] against [4 eager steps].  float32 convolutions
+    (no TF32), no dropout.  Only ONE replayed step is compared: Adam turns every gradient component that is pure rounding
+    noise into a +-lr step, and later steps amplify that - after 8 steps two equally correct implementations of the same
+    layer (cuDNN's BatchNormalization in the eager loop, ATen's under graph capture) agree on only 60 % of the parameters to
+    1e-4, after 40 steps on 3 % (`profiles/r2_train_variant_agreement.txt`), while their losses stay within 2 %.  So: the bulk
+    of the parameters after one replayed step, the worst element by a few learning rates, and the loss of a longer run."""
     import torch
     from othellozero_b200 import net, train
     monkeypatch.setattr(train, "GRAPH_MIN_BATCHES", 1)
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     n, C, lr = 6, 128, 1e-3
     blob = net.init_weights(n, C, seed=5)
-    agree = lambda a, b: float(np.mean(np.abs(a - b) < 1e-4))
-    for full_batches, ragged in ((4, 0), (7, 5)):
+    for full_batches, ragged in ((4, 0), (24, 5)):
         arrays = _arrays(n, 32 * full_batches + ragged, 6 + full_batches)
         outs = []
-        for graph in (False, False, True):
+        for graph in (False, True):
             new, hist = train.train_blob(blob, arrays, n, C, epochs=1, batch_size=32, lr=lr, dropout=0.0, device="cuda", seed=3,
                                          cuda_graph=graph)
             assert np.isfinite(new).all() and np.isfinite(np.array(hist)).all()
             outs.append((new, np.array(hist)))
         steps = full_batches + (1 if ragged else 0)
         assert not np.array_equal(outs[0][0], blob)
-        noise, got = agree(outs[0][0], outs[1][0]), agree(outs[0][0], outs[2][0])
-        assert got >= 0.9 * noise - 0.02, (full_batches, "eager vs eager", noise, "eager vs graph", got)
-        assert np.abs(outs[0][0] - outs[2][0]).max() <= 2 * lr * steps + 1e-4
-        assert np.allclose(outs[0][1], outs[2][1], rtol=5e-2), (outs[0][1], outs[2][1])
+        d = np.abs(outs[0][0] - outs[1][0])
+        if full_batches == 4:
+            assert np.mean(d < 1e-4) > 0.95, np.mean(d < 1e-4)
+        assert d.max() <= 2 * lr * steps + 1e-4
+        assert np.allclose(outs[0][1], outs[1][1], rtol=4e-2), (outs[0][1], outs[1][1])
 
 
 def test_trained_blob_loads_into_the_device_tower():
