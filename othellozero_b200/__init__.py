@@ -8,8 +8,10 @@ the modules here mirror the reference's own classes and functions:
     net       B200NNet, NeuralNets, weight-blob helpers       (Net/NNet.py, Net/OthelloNN.py)
     selfplay  execute_episode(s), SelfPlay, make_b200_worker  (training.py:13-72, workers.py:24-79)
     arena     agents, duel_between_agents, pit                (agents.py)
+    buffer    CircularArray, RecordBuffer (replay buffer)     (main.py:21-53)
     train     train_blob (PyTorch autograd)                   (Net/NNet.py:53-68)
     dist      broadcast_weights, gather_examples (NCCL)       (workers.py:203-296,180-184)
+    iteration one whole training iteration on the node        (main.py:71-148)
     engine    thin numpy handle on the C-ABI
 
 Build the library with ``python -m othellozero_b200.build`` (nvcc, -gencode arch=compute_100a,code=sm_100a).
